@@ -1,0 +1,276 @@
+"""Seeded synthetic workloads: hypernet configs at the BASELINE shapes, random
+weights with the reference's ``state_dict`` names, source-embedding tables, hn tokenizers (Unigram / BPE)
+and byte-level target vocabularies.  No real tokenizer or checkpoint is reachable offline (the reference's
+``artifacts/tokenizers/*/tokenizer.json`` are Git-LFS pointers), so tests, ``smoke()`` and ``bench.py``
+all draw from these generators.  numpy ``default_rng`` keeps the streams identical on every box.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .config import ZettHypernetConfig
+
+# --------------------------------------------------------------------------------------------------
+# configs (hyper-parameters from the reference's shipped configs)
+# --------------------------------------------------------------------------------------------------
+_SHAPES = {
+    # name: dict(n_embd, hidden, intermediate, heads, lang_id, n_langs, pad, v0, separate, n_extra)
+    "tiny": dict(n_embd=64, hn_hidden_size=128, hn_intermediate_size=256, hn_num_attention_heads=None,
+                 hn_embed_lang_id=False, n_langs=None, pad_token_id=2, original_vocab_size=300,
+                 separate_out_embeddings=True, hn_n_extra_tokens=16),
+    "tiny_lang": dict(n_embd=128, hn_hidden_size=128, hn_intermediate_size=256, hn_num_attention_heads=4,
+                      hn_embed_lang_id=True, n_langs=5, pad_token_id=1, original_vocab_size=300,
+                      separate_out_embeddings=False, hn_n_extra_tokens=0),
+    # configs/zeroshot/v7:xlmr:multilingual_long:lw=0.5_26l.json:61,66-67
+    "xlmr": dict(n_embd=768, hn_hidden_size=768, hn_intermediate_size=1536, hn_num_attention_heads=None,
+                 hn_embed_lang_id=True, n_langs=26, pad_token_id=1, original_vocab_size=250002,
+                 separate_out_embeddings=False, hn_n_extra_tokens=256),
+    # configs/zeroshot/v7:tinyllama_en+code:lw=0.5_long.json:57-58
+    "tinyllama": dict(n_embd=2048, hn_hidden_size=2048, hn_intermediate_size=4096, hn_num_attention_heads=None,
+                      hn_embed_lang_id=False, n_langs=None, pad_token_id=2, original_vocab_size=32000,
+                      separate_out_embeddings=True, hn_n_extra_tokens=256),
+    # configs/zeroshot/v7:mistral7b_en+code:lw=0.5_long.json:58-60
+    "mistral": dict(n_embd=4096, hn_hidden_size=4096, hn_intermediate_size=8192, hn_num_attention_heads=32,
+                    hn_embed_lang_id=False, n_langs=None, pad_token_id=2, original_vocab_size=32000,
+                    separate_out_embeddings=True, hn_n_extra_tokens=256),
+}
+
+
+def make_config(name: str, **overrides) -> ZettHypernetConfig:
+    kw = dict(
+        hn_model_name_or_path="roberta-base", hn_surface_maxlen=7, hn_n_layers=3,
+        hn_rescale_embeddings=True, hn_embed_using_source_embeddings=True, hn_predict_bias=True,
+    )
+    kw.update(_SHAPES[name])
+    kw.update(overrides)
+    return ZettHypernetConfig(**kw)
+
+
+def config_names() -> List[str]:
+    return list(_SHAPES)
+
+
+# --------------------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------------------
+def weight_shapes(cfg: ZettHypernetConfig) -> Dict[str, Tuple[int, ...]]:
+    """The reference's ``state_dict`` names and shapes (hf_hypernet/modeling_hypernet.py:46-154)."""
+    H, I, D = cfg.hn_hidden_size, cfg.hn_intermediate_size, cfg.n_embd
+    E = cfg.n_in_embd
+    s: Dict[str, Tuple[int, ...]] = {}
+    s["model.embeddings.word_embeddings.weight"] = (cfg.pad_token_id + 1, H)
+    s["model.embeddings.token_type_embeddings.weight"] = (1, H)
+    s["model.embeddings.position_embeddings.weight"] = (514, H)
+    s["model.embeddings.LayerNorm.weight"] = (H,)
+    s["model.embeddings.LayerNorm.bias"] = (H,)
+    for l in range(cfg.hn_n_layers):
+        p = f"model.encoder.layer.{l}."
+        for n in ("query", "key", "value"):
+            s[p + f"attention.self.{n}.weight"] = (H, H)
+            s[p + f"attention.self.{n}.bias"] = (H,)
+        s[p + "attention.output.dense.weight"] = (H, H)
+        s[p + "attention.output.dense.bias"] = (H,)
+        s[p + "attention.output.LayerNorm.weight"] = (H,)
+        s[p + "attention.output.LayerNorm.bias"] = (H,)
+        s[p + "intermediate.dense.weight"] = (I, H)
+        s[p + "intermediate.dense.bias"] = (I,)
+        s[p + "output.dense.weight"] = (H, I)
+        s[p + "output.dense.bias"] = (H,)
+        s[p + "output.LayerNorm.weight"] = (H,)
+        s[p + "output.LayerNorm.bias"] = (H,)
+    s["fallback_embeddings.weight"] = (max(cfg.hn_n_extra_tokens, 1), E)
+    s["input_projection.0.weight"] = (H, E)
+    s["input_projection.0.bias"] = (H,)
+
+    def projector(prefix):
+        s[prefix + "dense1.weight"] = (I, H)
+        s[prefix + "dense1.bias"] = (I,)
+        s[prefix + "dense2.weight"] = (H, I)
+        s[prefix + "dense2.bias"] = (H,)
+        s[prefix + "ln.weight"] = (H,)
+        s[prefix + "ln.bias"] = (H,)
+
+    projector("input_projection.1.")
+    projector("output_projection.0.")
+    s["output_projection.1.weight"] = (E if cfg.hn_single_head else D, H)
+    s["output_projection.1.bias"] = (E if cfg.hn_single_head else D,)
+    if cfg.separate_out_embeddings and not cfg.hn_single_head:
+        projector("output_projection_out.0.")
+        s["output_projection_out.1.weight"] = (D, H)
+        s["output_projection_out.1.bias"] = (D,)
+    if cfg.hn_rescale_embeddings:
+        s["in_scaler.w"] = (1, E)
+        s["in_scaler.b"] = (1, E)
+        s["scaler.w"] = (1, D)
+        s["scaler.b"] = (1, D)
+        if cfg.separate_out_embeddings:
+            s["out_scaler.w"] = (1, D)
+            s["out_scaler.b"] = (1, D)
+    if cfg.hn_predict_bias:
+        s["bias_projection.weight"] = (1, H)
+        s["bias_projection.bias"] = (1,)
+    if cfg.hn_embed_lang_id:
+        s["lang_embeddings.weight"] = (cfg.n_langs, H)
+    return s
+
+
+def make_weights(cfg: ZettHypernetConfig, seed: int = 0) -> Dict[str, np.ndarray]:
+    """Random fp32 weights: Linear W ~ N(0, 1/fan_in), biases ~ N(0, 0.02^2),
+    LayerNorm gamma = 1 + 0.1 N(0,1), beta = 0.1 N(0,1), embeddings ~ N(0, 0.02^2),
+    scalers w ~ U(0.5, 1.5), b ~ N(0, 0.02^2)."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in weight_shapes(cfg).items():
+        leaf = name.rsplit(".", 1)[-1]
+        if "LayerNorm" in name or ".ln." in name:
+            if leaf == "weight":
+                w = 1.0 + 0.1 * rng.standard_normal(shape, dtype=np.float32)
+            else:
+                w = 0.1 * rng.standard_normal(shape, dtype=np.float32)
+        elif "scaler" in name:
+            if leaf == "w":
+                w = rng.uniform(0.5, 1.5, size=shape).astype(np.float32)
+            else:
+                w = 0.02 * rng.standard_normal(shape, dtype=np.float32)
+        elif "embeddings" in name:
+            w = 0.02 * rng.standard_normal(shape, dtype=np.float32)
+        elif leaf == "bias":
+            w = 0.02 * rng.standard_normal(shape, dtype=np.float32)
+        else:  # Linear weight [out, in]
+            w = rng.standard_normal(shape, dtype=np.float32) / np.float32(np.sqrt(shape[-1]))
+        out[name] = np.ascontiguousarray(w, dtype=np.float32)
+    return out
+
+
+def make_source_embeddings(cfg: ZettHypernetConfig, seed: int = 100, n_rows: Optional[int] = None) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    v0 = cfg.original_vocab_size if n_rows is None else n_rows
+    return (0.02 * rng.standard_normal((v0, cfg.n_in_embd), dtype=np.float32)).astype(np.float32)
+
+
+def make_random_surface_forms(cfg: ZettHypernetConfig, n_rows: int, seed: int = 7,
+                              p_fallback: float = 0.05, full_rows: bool = False) -> np.ndarray:
+    """Random int32 [n_rows, L] surface forms with a prefix of ids and a pad tail, fallback ids mixed in,
+    one fully padded row and one row whose position 0 is the pad id (edge cases of SURVEY 8a)."""
+    rng = np.random.default_rng(seed)
+    L = cfg.hn_surface_maxlen
+    v0, nx, pad = cfg.original_vocab_size, cfg.hn_n_extra_tokens, cfg.pad_token_id
+    ids = rng.integers(0, v0, size=(n_rows, L)).astype(np.int32)
+    ids[ids == pad] = pad + 1
+    if nx > 0:
+        fb = rng.random((n_rows, L)) < p_fallback
+        ids[fb] = (v0 + rng.integers(0, nx, size=int(fb.sum()))).astype(np.int32)
+    if not full_rows:
+        lens = rng.integers(1, L + 1, size=n_rows)
+        ids[np.arange(L)[None, :] >= lens[:, None]] = pad
+        if n_rows > 3:
+            ids[3, :] = pad            # fully masked row (or lang slot only)
+        if n_rows > 5:
+            ids[5, 0] = pad            # pad in position 0, real ids after it
+            ids[5, 1] = pad + 1
+    return ids
+
+
+# --------------------------------------------------------------------------------------------------
+# byte alphabet (GPT-2 byte <-> unicode table; reference zett/utils.py:351-609)
+# --------------------------------------------------------------------------------------------------
+def _bytes_to_chars() -> Dict[int, str]:
+    keep = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
+    table, n = {}, 0
+    for b in range(256):
+        if b in keep:
+            table[b] = chr(b)
+        else:
+            table[b] = chr(256 + n)
+            n += 1
+    return table
+
+
+BYTES_TO_CHARS: Dict[int, str] = _bytes_to_chars()
+CHARS_TO_BYTES: Dict[str, int] = {c: b for b, c in BYTES_TO_CHARS.items()}
+
+SPECIALS = ["<s>", "<pad>", "</s>", "<unk>"]
+
+
+def _random_pieces(n: int, seed: int) -> List[str]:
+    """Distinct random lowercase pieces, length min(16, max(2, Geometric(0.25))), half prefixed with G-dot."""
+    rng = np.random.default_rng(seed)
+    space = BYTES_TO_CHARS[32]
+    seen, out = set(), []
+    while len(out) < n:
+        m = n - len(out)
+        lens = np.minimum(16, np.maximum(2, rng.geometric(0.25, size=m)))
+        pref = rng.random(m) < 0.5
+        letters = rng.integers(97, 123, size=(m, 16))
+        for i in range(m):
+            s = (space if pref[i] else "") + "".join(map(chr, letters[i, : lens[i]]))
+            if s not in seen:
+                seen.add(s)
+                out.append(s)
+    return out
+
+
+def make_hn_vocab(n_vocab: int = 32000, seed: int = 1):
+    """hn-tokenizer vocabulary: 4 specials + 256 alphabet chars + random pieces; Unigram scores
+    -U(4, 11) for pieces and -12 for single chars (specials 0)."""
+    rng = np.random.default_rng(seed + 1000)
+    alphabet = [BYTES_TO_CHARS[b] for b in range(256)]
+    pieces = _random_pieces(n_vocab - len(SPECIALS) - 256, seed)
+    vocab = SPECIALS + alphabet + pieces
+    scores = np.concatenate([
+        np.zeros(len(SPECIALS)), np.full(256, -12.0), -rng.uniform(4.0, 11.0, size=len(pieces))])
+    return vocab, scores.astype(np.float64)
+
+
+def make_bpe_merges(vocab: List[str]) -> Tuple[List[str], List[Tuple[str, str]]]:
+    """Derive a BPE merge list by greedy left-to-right pair merges of each multi-char piece; any
+    intermediate symbol missing from the vocabulary is appended to it."""
+    vocab = list(vocab)
+    index = {t: i for i, t in enumerate(vocab)}
+    merges, seen = [], set()
+    for piece in list(vocab):
+        if piece in SPECIALS or len(piece) < 2:
+            continue
+        left = piece[0]
+        for ch in piece[1:]:
+            if (left, ch) not in seen:
+                seen.add((left, ch))
+                merges.append((left, ch))
+            left = left + ch
+            if left not in index:
+                index[left] = len(vocab)
+                vocab.append(left)
+    return vocab, merges
+
+
+def make_hn_tokenizer(kind: str = "unigram", n_vocab: int = 32000, seed: int = 1, pad_token: str = "</s>"):
+    """A ``PreTrainedTokenizerFast`` wrapping a synthetic Unigram or BPE model, as ``tokenizer_to_use``."""
+    from tokenizers import Tokenizer, models
+    from transformers import PreTrainedTokenizerFast
+
+    vocab, scores = make_hn_vocab(n_vocab, seed)
+    if kind == "unigram":
+        model = models.Unigram([(t, float(s)) for t, s in zip(vocab, scores)], unk_id=3, byte_fallback=False)
+    elif kind == "bpe":
+        vocab, merges = make_bpe_merges(vocab)
+        model = models.BPE(vocab={t: i for i, t in enumerate(vocab)}, merges=merges, unk_token="<unk>")
+    else:
+        raise ValueError(kind)
+    return PreTrainedTokenizerFast(tokenizer_object=Tokenizer(model), bos_token="<s>", pad_token=pad_token,
+                                   eos_token="</s>", unk_token="<unk>")
+
+
+def make_target_tokens(n_tokens: int, seed: int = 2, specials: Tuple[str, ...] = ("</s>",)) -> List[str]:
+    """'GPT2-style' byte-level target vocabulary: special token(s) + 256 chars + random pieces."""
+    alphabet = [BYTES_TO_CHARS[b] for b in range(256)]
+    base = list(specials) + alphabet
+    if n_tokens <= len(base):
+        return base[:n_tokens]
+    return base + _random_pieces(n_tokens - len(base), seed)
+
+
+def length_histogram(surface_forms: np.ndarray, pad_token_id: int) -> List[int]:
+    n = (np.asarray(surface_forms) != pad_token_id).sum(axis=1)
+    return np.bincount(n, minlength=surface_forms.shape[1] + 1).tolist()
