@@ -1,0 +1,197 @@
+// Persistent, warp-specialised tcgen05 GEMM for the hypernetwork's Linear layers:
+//     out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )          (nn.Linear: y = x W^T + b, both operands K-major)
+//
+//  * operands are 16-bit "planes": plane 0 = round(x), plane 1 = round(x - plane0)  (bf16 or fp16).
+//    n_terms == 1 issues A0*B0 only; n_terms == 3 issues A0*B0 + A1*B0 + A0*B1 into the SAME TMEM accumulator,
+//    which restores ~fp32 operand precision (the 1e-3 parity budget rules out single-pass bf16).
+//  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}, 128B swizzle), warp 1 = MMA issuer + TMEM owner,
+//    warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / residual / column affine -> fp32 and/or split planes).
+//  * accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+//    main loop of tile i+1; smem stages form an mbarrier ring.
+//  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the
+//    B tile; the leader issues the MMAs and multicasts the commits.
+//  * M may live in device memory (packed-token counts are data dependent); tiles beyond it are skipped.
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+namespace zett {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;         // 64 x 2 B = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kMaxStages = 8;
+constexpr int kGemmThreads = 192;   // 6 warps
+constexpr int kGroupM = 16;         // m-tiles per rasterisation group (L2 reuse of the W panel)
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmShape {
+  int m_host;          // rows of A / out when m_dev == nullptr
+  const int* m_dev;    // optional device-resident row count
+  int n, k;
+  int block_n;         // 32, 64, 128 or 256
+  int n_terms;         // 1 or 3
+  int n_planes;        // planes held by the tensor maps' boxes (1 or 2)
+  uint32_t idesc;      // tcgen05 instruction descriptor
+  int num_stages;
+  uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;
+};
+
+struct TileCoord { int m_blk, n_blk; };
+
+__device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_tiles) {
+  const int group_tiles = kGroupM * n_tiles;
+  const int g = tile / group_tiles;
+  const int first_m = g * kGroupM;
+  const int gm = min(kGroupM, m_tiles - first_m);
+  const int r = tile - g * group_tiles;
+  TileCoord c;
+  c.m_blk = first_m + r % gm;
+  c.n_blk = r / gm;
+  return c;
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmShape s, const EpilogueParams ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + s.num_stages * s.stage_bytes;
+  auto full_bar = [&](int i) { return bar_base + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_base + 8u * (kMaxStages + i); };
+  auto tmem_full_bar = [&](int i) { return bar_base + 8u * (2 * kMaxStages + i); };
+  auto tmem_empty_bar = [&](int i) { return bar_base + 8u * (2 * kMaxStages + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  const int M = s.m_dev ? *s.m_dev : s.m_host;
+  const int tile_m = kBlockM * CG;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
+  const int n_tiles = (s.n + s.block_n - 1) / s.block_n;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = (s.k + kBlockK - 1) / kBlockK;
+  const int first_tile = blockIdx.x / CG;
+  const int tile_step = gridDim.x / CG;
+  const int load_n = s.block_n / CG;  // rows of the W tile this CTA stages
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int i = 0; i < s.num_stages; ++i) {
+      mbar_init(full_bar(i), CG);   // one arrive(+tx) per producing CTA, all on the leader's barrier
+      mbar_init(empty_bar(i), 1);   // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full_bar(i), 1);
+      mbar_init(tmem_empty_bar(i), 128 * CG);  // every epilogue thread of every CTA in the group
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================== TMA producer ==========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const TileCoord tc = tile_coord(tile, m_tiles, n_tiles);
+        const int row_a = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
+        const int row_b = tc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+          const uint32_t a_dst = smem_base + stage * s.stage_bytes;
+          const uint32_t b_dst = a_dst + s.n_planes * s.a_plane_bytes;
+          if constexpr (CG == 1) {
+            mbar_expect_tx(full_bar(stage), s.stage_bytes);
+            tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * kBlockK, row_a, 0);
+            tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * kBlockK, row_b, 0);
+          } else {
+            if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
+            else mbar_arrive_cluster(full_bar(stage), 0);
+            tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * kBlockK, row_a, 0);
+            tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * kBlockK, row_b, 0);
+          }
+          if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    if (lane == 0 && leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * s.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase, 3);
+          tc_fence_after();
+          const uint32_t a0 = smem_base + stage * s.stage_bytes;
+          const uint32_t b0 = a0 + s.n_planes * s.a_plane_bytes;
+          const uint64_t da0 = umma_desc_sw128(a0), db0 = umma_desc_sw128(b0);
+          const uint64_t da1 = umma_desc_sw128(a0 + s.a_plane_bytes), db1 = umma_desc_sw128(b0 + s.b_plane_bytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+            const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
+            umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
+            if (s.n_terms == 3) {
+              umma_f16<CG>(tmem_d, da1 + koff, db0 + koff, s.idesc, 1u);
+              umma_f16<CG>(tmem_d, da0 + koff, db1 + koff, s.idesc, 1u);
+            }
+          }
+          umma_commit<CG>(empty_bar(stage));                       // frees the smem stage (both CTAs)
+          if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc));  // accumulator complete
+          if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue warps ========================================
+    const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32) are the ones this warp may read
+    int iter = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
+      const TileCoord tc = tile_coord(tile, m_tiles, n_tiles);
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+      mbar_wait(tmem_full_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      const int row = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
+      const int col_tile = tc.n_blk * s.block_n;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
+      for (int c = 0; c < s.block_n; c += 32) {
+        float v[32];
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+        tmem_ld_wait();
+        const int col0 = col_tile + c;
+        if (row < M && col0 < s.n) epilogue_store32(ep, row, col0, min(32, s.n - col0), v);
+      }
+      tc_fence_before();
+      if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
+      else mbar_arrive_cluster(tmem_empty_bar(acc), 0);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
+}
+
+}  // namespace zett
