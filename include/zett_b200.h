@@ -1,0 +1,176 @@
+/*
+ * zett_b200 -- C ABI of the B200-native ZeTT embedding-prediction hot path (libzett_b200.so).
+ *
+ * The reference (bminixhofer/zett) has no FFI on this path: its boundary is a Python call surface.  Every entry
+ * point below names the reference interface it replaces; `INTEGRATION.md` shows the ctypes stubs a maintainer of the
+ * reference would add.  Conventions:
+ *   - plain pointers and sizes only (no torch types); every pointer is BORROWED -- the caller keeps the memory
+ *     alive until the CUDA stream it passed has been synchronised;
+ *   - every function returns 0 on success or a negative zett_status; nothing throws across the ABI; the message of
+ *     the last failure on the calling thread is available from zett_last_error();
+ *   - a handle is bound to the CUDA device that was current when it was created and is not thread-safe
+ *     (one handle per device, one caller at a time); all device work is enqueued on the stream passed in.
+ */
+#ifndef ZETT_B200_H_
+#define ZETT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZETT_B200_ABI_VERSION 1
+
+typedef enum zett_status {
+  ZETT_OK = 0,
+  ZETT_ERR_INVALID = -1,       /* bad argument / shape / name                                   (ValueError)          */
+  ZETT_ERR_UNSUPPORTED = -2,   /* a branch the reference raises NotImplementedError for         (NotImplementedError) */
+  ZETT_ERR_CUDA = -3,          /* CUDA runtime / driver failure, incl. "no device"              (RuntimeError)        */
+  ZETT_ERR_STATE = -4,         /* call order (forward before finalize, missing weight ...)      (RuntimeError)        */
+  ZETT_ERR_INDEX = -5,         /* a surface-form id outside [0, original_vocab_size + n_extra)  (IndexError)          */
+  ZETT_ERR_KEY = -6,           /* a token char outside the 256-char byte alphabet               (KeyError)            */
+  ZETT_ERR_MISSING_UNK = -7    /* Unigram needed <unk> but the model has no unk id              (Exception)           */
+} zett_status;
+
+const char* zett_last_error(void);
+int zett_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Hypernetwork forward.
+ * Replaces ZettHypernet.__init__ / __call__   (reference hf_hypernet/modeling_hypernet.py:46-154, 156-267)
+ *      ==  Hypernet.setup / __call__          (reference zett/model/__init__.py:217-346, 387-469).
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Mirrors ZettHypernetConfig (reference hf_hypernet/configuration_hypernet.py:4-56) plus the fields training writes
+ * onto it (train.py:295,314,350,361).  Booleans are 0/1 ints. */
+typedef struct zett_hn_config {
+  int32_t struct_bytes;                    /* sizeof(zett_hn_config), ABI guard                                    */
+  int32_t hn_surface_maxlen;               /* L                                                                    */
+  int32_t hn_n_layers;
+  int32_t n_embd;                          /* D                                                                    */
+  int32_t hn_hidden_size;                  /* H                                                                    */
+  int32_t hn_intermediate_size;            /* I                                                                    */
+  int32_t hn_num_attention_heads;          /* 0 -> H / 64        (modeling_hypernet.py:73-75)                      */
+  int32_t hn_rescale_embeddings;
+  int32_t hn_embed_target_priors;          /* must be 0          (modeling_hypernet.py:85-89)                      */
+  int32_t hn_add_inter_token_attention;    /* must be 0          (modeling_hypernet.py:85-89)                      */
+  int32_t hn_embed_using_source_embeddings;/* must be 1          (modeling_hypernet.py:167-168)                    */
+  int32_t hn_concat_last_hidden_state;     /* must be 0          (shape-inconsistent in the reference)             */
+  int32_t hn_single_head;
+  int32_t hn_predict_bias;
+  int32_t hn_embed_lang_id;
+  int32_t hn_model_type_is_roberta;        /* must be 1          (modeling_hypernet.py:78-79)                      */
+  int32_t n_langs;
+  int32_t pad_token_id;
+  int32_t original_vocab_size;             /* V0                                                                   */
+  int32_t hn_n_extra_tokens;
+  int32_t separate_out_embeddings;
+  int32_t max_position_embeddings;         /* rows of model.embeddings.position_embeddings (514 for roberta-base)  */
+  float encoder_layer_norm_eps;            /* 1e-5 (roberta-base)                                                  */
+  /* execution knobs, not model semantics */
+  int32_t max_rows_per_pass;               /* rows handled by one pass of the kernels (0 -> 16384, transfer.py:44) */
+  int32_t gemm_impl;                       /* 0 = auto (tcgen05 2-CTA), 1 = tcgen05 1-CTA, 2 = tcgen05 2-CTA,
+                                              3 = SIMT fp32 debug kernel (checker, never the default)              */
+  int32_t split_terms;                     /* 0/3 = 3-term bf16 split (fp32-class accuracy), 1 = single bf16 pass  */
+} zett_hn_config;
+
+typedef struct zett_hn zett_hn;
+
+/* dtype codes for zett_hn_set_weight */
+#define ZETT_F32 0
+#define ZETT_F16 1
+#define ZETT_BF16 2
+
+int zett_hn_create(const zett_hn_config* cfg, zett_hn** out);
+
+/* `name` is a key of the reference's PyTorch state_dict (e.g. "model.encoder.layer.0.attention.self.query.weight",
+ * "input_projection.1.dense1.weight", "in_scaler.w"; full list in SURVEY.md section 8b).  `data` may be a host or a
+ * device pointer; it is copied before the call returns.  Unused reference keys ("model.embeddings.word_embeddings.
+ * weight", "*.position_ids", "*.token_type_ids") are accepted and ignored. */
+int zett_hn_set_weight(zett_hn* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
+
+/* Checks that every weight the config needs is present, splits the Linear weights into the 16-bit planes the
+ * tensor-core kernels consume, builds the TMA descriptors, frees the staging copies. */
+int zett_hn_finalize(zett_hn* h);
+
+/* Bytes of device workspace a forward of `n_rows` rows uses (allocated lazily by the library, reused across calls). */
+size_t zett_hn_workspace_bytes(const zett_hn* h, int64_t n_rows);
+
+/* pred_in[n_rows, D], pred_out[n_rows, D] (NULL unless separate_out_embeddings), pred_bias[n_rows]  <-
+ *     ZettHypernet.__call__(target_surface_forms[n_rows, L] int32, source_embeddings[v0_rows, E] fp32, lang_index)
+ * All five pointers are DEVICE pointers, row-major.  lang_index < 0 means None.
+ * ld_pred = elements between consecutive rows of pred_in / pred_out (0 -> D, i.e. contiguous; otherwise a multiple
+ * of 4 and >= D), ld_bias = elements between consecutive pred_bias entries (0 -> 1): a caller that row-shards the
+ * vocabulary lets all three land in one [n_rows, 2D + 4] block so that a single all-gather moves them.
+ * Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = legacy default stream); the call does not synchronise. */
+int zett_hn_forward(zett_hn* h, const int32_t* surface_forms_dev, int64_t n_rows, const float* source_emb_dev,
+                    int64_t v0_rows, int32_t lang_index, float* pred_in_dev, float* pred_out_dev,
+                    float* pred_bias_dev, int64_t ld_pred, int64_t ld_bias, void* cuda_stream);
+
+/* Synchronises `cuda_stream` and reports what the kernels recorded: ZETT_ERR_INDEX if any surface-form id was
+ * outside [0, V0 + max(n_extra, 1)) (the reference would raise an index error), ZETT_ERR_CUDA on a kernel fault. */
+int zett_hn_check(zett_hn* h, void* cuda_stream);
+
+/* Execution statistics of the last forward: kernels launched, packed (non-pad) positions, rows. */
+typedef struct zett_hn_stats {
+  int64_t kernel_launches;
+  int64_t rows;
+  int64_t packed_positions;    /* valid after zett_hn_check (read back from the device)                            */
+  int64_t encoder_positions;
+  double flops_executed;       /* algorithmic FLOPs of the GEMMs actually issued (one count per product term set)  */
+  double gemm_ms;              /* summed CUDA-event time of the GEMM kernel launches (only with zett_hn_set_timing) */
+  int64_t gemm_launches;
+} zett_hn_stats;
+int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out);
+
+/* enable != 0: bracket every GEMM launch with CUDA events on the caller's stream; zett_hn_check then fills
+ * gemm_ms / gemm_launches of the last forward (the roofline figure of bench.py). */
+int zett_hn_set_timing(zett_hn* h, int enable);
+
+void zett_hn_destroy(zett_hn* h);
+
+/* Stand-alone entry to the GEMM engine (used by the unit tests and the micro-benchmark):
+ *   out[m, n] = act(A[m, k] . W[n, k]^T + bias[n])     A, W, out fp32 device pointers, row-major.
+ * impl / split_terms as in zett_hn_config; act: 0 none, 1 gelu(tanh), 2 gelu(erf). `elapsed_ms` (nullable) receives
+ * the CUDA-event time of `iters` back-to-back launches of the GEMM kernel alone (operands already split). */
+int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev, float* out_dev, int64_t m, int64_t n,
+                  int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Surface forms.
+ * Replaces get_surface_form_matrix                  (reference zett/utils.py:651-689)
+ * and the tokenizers.models.{Unigram,BPE}.tokenize call it makes per token (zett/utils.py:681; third-party Rust).
+ * Host-side, multi-threaded C++; strings are UTF-8, NUL-terminated.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct zett_tok zett_tok;
+
+/* Unigram model: pieces[n] with scores[n]; unk_id < 0 = None. */
+int zett_tok_create_unigram(const char* const* pieces, const double* scores, int64_t n, int64_t unk_id,
+                            int byte_fallback, zett_tok** out);
+
+/* BPE model: vocab[n] (index = id); merges as m pairs of ids (left, right) in rank order.  unk_id < 0 = None.
+ * continuing_subword_prefix / end_of_word_suffix may be NULL. */
+int zett_tok_create_bpe(const char* const* vocab, int64_t n, const int32_t* merges, int64_t m, int64_t unk_id,
+                        const char* continuing_subword_prefix, const char* end_of_word_suffix, int fuse_unk,
+                        int byte_fallback, int ignore_merges, zett_tok** out);
+
+/* ids of one token string (Model.tokenize); returns the number of ids (may exceed `cap`; only `cap` are written)
+ * or a negative zett_status. */
+int64_t zett_tok_tokenize(const zett_tok* t, const char* token, int32_t* out_ids, int64_t cap);
+
+/* out[v + padding, maxlen] int32 (host), pre-filled by the callee with pad_id.
+ * special_ids[i] >= 0 marks tokens[i] as one of the hn tokenizer's special tokens with that id (written to column 0);
+ * special_ids may be NULL.  Tokens holding a char outside the 256-char byte alphabet fail with ZETT_ERR_KEY
+ * (the reference raises KeyError at zett/utils.py:675).  n_threads <= 0 -> hardware concurrency. */
+int zett_surface_forms(const zett_tok* t, const char* const* tokens, int64_t v, const int32_t* special_ids,
+                       int32_t maxlen, int32_t pad_id, int64_t padding, int32_t* out, int64_t* n_truncated,
+                       int n_threads);
+
+void zett_tok_destroy(zett_tok* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZETT_B200_H_ */

@@ -56,8 +56,9 @@ def layer_norm(x, w, b, eps):
 
 
 def linear(x, w, b):
-    """``nn.Linear``: y = x W^T + b with W [out, in]."""
-    return x @ w.T + b
+    """``nn.Linear``: y = x W^T + b with W [out, in] (leading dims flattened into one GEMM, as ATen does)."""
+    y = x.reshape(-1, x.shape[-1]) @ w.T
+    return y.reshape(x.shape[:-1] + (w.shape[0],)) + b
 
 
 def projector_block(x, W, prefix):

@@ -1,0 +1,161 @@
+"""GPU self-test driver (run in a child process so that a kernel fault cannot poison the caller's CUDA context).
+
+    python tests/gpu_selftest.py gemm    --impl {1,2,3}
+    python tests/gpu_selftest.py forward --impl {1,2,3} [--configs tiny,tiny_lang,...] [--rows N]
+
+Prints one JSON object per line: GEMM cases are checked against a float64 torch matmul of the SAME fp32 inputs,
+forward cases against the numpy oracle (oracle/hypernet_oracle.py).  ``tests/test_gpu_*.py`` assert on the lines.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import hypernet_oracle as ho  # noqa: E402
+from zett_b200 import _lib, synthetic  # noqa: E402
+from zett_b200.modeling_hypernet import NativeHypernet  # noqa: E402
+
+GEMM_CASES = [
+    # m, n, k, act, terms
+    (128, 128, 64, 0, 3),
+    (128, 256, 128, 0, 3),
+    (256, 256, 256, 0, 3),
+    (200, 384, 192, 0, 3),      # ragged M, N = 3 x 128
+    (77, 64, 128, 1, 3),        # tiny M, gelu tanh
+    (1000, 768, 768, 2, 3),     # XLM-R shapes, gelu erf
+    (4096, 2304, 768, 0, 3),
+    (3000, 4096, 4096, 0, 3),   # Mistral H x H
+    (1024, 8192, 4096, 1, 3),
+    (1024, 4096, 8192, 0, 3),
+    (512, 256, 128, 0, 1),      # single-pass mode
+    (2048, 4096, 4096, 0, 1),
+]
+
+
+def run_gemm(impl: int):
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    ok = True
+    for (m, n, k, act, terms) in GEMM_CASES:
+        a = torch.randn(m, k, device=dev)
+        w = torch.randn(n, k, device=dev) / k ** 0.5
+        b = torch.randn(n, device=dev) * 0.1
+        out = torch.full((m, n), float("nan"), device=dev)
+        ms = ctypes.c_float(0)
+        iters = 3
+        try:
+            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, act, impl, terms,
+                                         iters, ctypes.byref(ms), None))
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps(dict(kind="gemm", impl=impl, m=m, n=n, k=k, act=act, terms=terms, error=str(e))), flush=True)
+            return False
+        ref = a.double() @ w.double().T + b.double()
+        if act == 1:
+            ref = torch.nn.functional.gelu(ref, approximate="tanh")
+        elif act == 2:
+            ref = torch.nn.functional.gelu(ref)
+        err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+        fro = ((out.double() - ref).norm() / ref.norm()).item()
+        tol = 5e-5 if terms == 3 else 2e-2
+        good = bool(np.isfinite(err) and err < tol)
+        ok &= good
+        tflops = 2.0 * m * n * k * iters / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+        print(json.dumps(dict(kind="gemm", impl=impl, m=m, n=n, k=k, act=act, terms=terms, max_rel=err, fro_rel=fro,
+                              ok=good, ms_per_launch=ms.value / iters, tflops=tflops)), flush=True)
+    return ok
+
+
+def forward_case(name, impl, rows, lang, overrides=None, max_rows_per_pass=0, seed=13, terms=0):
+    dev = torch.device("cuda", 0)
+    cfg = synthetic.make_config(name, **(overrides or {}))
+    weights = synthetic.make_weights(cfg, seed=11)
+    big = cfg.original_vocab_size > 100000
+    src = synthetic.make_source_embeddings(cfg, seed=12)
+    sf = synthetic.make_random_surface_forms(cfg, rows, seed=seed)
+    t0 = time.time()
+    want = ho.hypernet_forward(cfg, weights, sf, src, lang_index=lang)
+    t_oracle = time.time() - t0
+    nat = NativeHypernet(cfg, weights, dev, max_rows_per_pass=max_rows_per_pass, gemm_impl=impl, split_terms=terms)
+    sf_d = torch.from_numpy(sf).to(dev)
+    src_d = torch.from_numpy(src).to(dev)
+    D = cfg.n_embd
+    pred_in = torch.full((rows, D), float("nan"), device=dev)
+    pred_out = torch.full((rows, D), float("nan"), device=dev) if cfg.separate_out_embeddings else None
+    bias = torch.full((rows,), float("nan"), device=dev)
+    res = dict(kind="forward", config=name, impl=impl, rows=rows, overrides=overrides or {}, pass_rows=max_rows_per_pass,
+               oracle_s=round(t_oracle, 3), big_table=big)
+    try:
+        nat.forward_into(sf_d, src_d, -1 if lang is None else lang, pred_in, pred_out, bias)
+        nat.check()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        nat.forward_into(sf_d, src_d, -1 if lang is None else lang, pred_in, pred_out, bias)
+        nat.check()
+        res["gpu_s"] = round(time.time() - t0, 4)
+    except Exception as e:  # noqa: BLE001
+        res["error"] = str(e)
+        print(json.dumps(res), flush=True)
+        return False
+    masked = ho.fully_masked_rows(cfg, sf)
+    ok = True
+    for key, g, w in (("pred_in", pred_in, want[0]), ("pred_out", pred_out, want[1]), ("pred_bias", bias, want[2])):
+        if w is None:
+            continue
+        gn = g.cpu().numpy()
+        fro, worst = ho.rel_errors(gn, w, exclude=masked)
+        res[key] = [fro, worst]
+        ok &= bool(np.isfinite(gn).all() and fro < 1e-3 and worst < 1e-3)
+        if masked.any():
+            mfro, mworst = ho.rel_errors(gn[masked], w[masked])
+            res[key + "_masked_rows"] = [mfro, mworst]
+    res["stats"] = nat.stats()
+    res["ok"] = ok
+    print(json.dumps(res), flush=True)
+    nat.close()
+    return ok
+
+
+FORWARD_CASES = {
+    # name: (config, rows, lang, overrides)
+    "tiny": ("tiny", 64, None, None),
+    "tiny_lang": ("tiny_lang", 64, 3, None),
+    "tiny_single_head": ("tiny", 48, None, {"hn_single_head": True}),
+    "tiny_plain": ("tiny", 48, None, {"hn_rescale_embeddings": False, "hn_predict_bias": False,
+                                       "separate_out_embeddings": False, "hn_n_extra_tokens": 0}),
+    "tiny_one_layer": ("tiny", 40, None, {"hn_n_layers": 1}),
+    "tiny_multi_pass": ("tiny", 300, None, None),
+    "xlmr": ("xlmr", 512, 3, None),
+    "tinyllama": ("tinyllama", 256, None, None),
+    "mistral": ("mistral", 192, None, None),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["gemm", "forward"])
+    ap.add_argument("--impl", type=int, default=0)
+    ap.add_argument("--configs", default="tiny,tiny_lang,tiny_single_head,tiny_plain,tiny_one_layer,tiny_multi_pass")
+    ap.add_argument("--terms", type=int, default=0)
+    args = ap.parse_args()
+    if args.what == "gemm":
+        ok = run_gemm(args.impl or 2)
+    else:
+        ok = True
+        for c in args.configs.split(","):
+            name, rows, lang, ov = FORWARD_CASES[c]
+            ok &= forward_case(name, args.impl, rows, lang, ov, max_rows_per_pass=96 if c == "tiny_multi_pass" else 0,
+                               terms=args.terms)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+"""GPU parity tests proper (run with -m gpu on a B200): every compute call goes through the C ABI of
+libzett_b200.so and is compared with the oracle (oracle/) or a float64 torch matmul.
+
+The per-implementation sweeps run in child processes (tests/gpu_selftest.py) so that a fault in one kernel variant
+is reported as such instead of poisoning the CUDA context of the whole session."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def run_selftest(args, timeout=900):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_selftest.py")] + args, capture_output=True, text=True,
+                       timeout=timeout, cwd=ROOT)
+    lines = []
+    for ln in r.stdout.splitlines():
+        ln = ln.strip()
+        if ln.startswith("{"):
+            lines.append(json.loads(ln))
+    return r, lines
+
+
+@pytest.mark.parametrize("impl", [3, 1, 2])
+def test_gemm_engine(impl):
+    """tcgen05 1-CTA / 2-CTA and the SIMT checker against float64 matmul: 3-term split within 5e-5 of max |ref|."""
+    r, lines = run_selftest(["gemm", "--impl", str(impl)])
+    assert lines, r.stdout + r.stderr
+    for ln in lines:
+        assert "error" not in ln, ln
+        assert ln["ok"], ln
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("impl", [3, 1, 2])
+def test_forward_tiny_configs(impl):
+    """All tiny configurations (separate / tied heads, lang-id slot, single head, no rescale / bias, one layer,
+    multi-pass) against the oracle: Frobenius and worst-row relative error <= 1e-3."""
+    r, lines = run_selftest(["forward", "--impl", str(impl)])
+    assert len(lines) == 6, r.stdout + r.stderr
+    for ln in lines:
+        assert "error" not in ln, ln
+        assert ln["ok"], ln
+
+
+@pytest.mark.parametrize("config", ["xlmr", "tinyllama", "mistral"])
+def test_forward_baseline_shapes(config):
+    """The three BASELINE shapes on a few hundred rows against the oracle (default GEMM implementation)."""
+    r, lines = run_selftest(["forward", "--impl", "0", "--configs", config], timeout=1800)
+    assert len(lines) == 1, r.stdout + r.stderr
+    assert "error" not in lines[0], lines[0]
+    assert lines[0]["ok"], lines[0]
+
+
+# ---- in-process tests of the public Python surface (default implementation) ---------------------------------------
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch
+
+
+def _model(torch, name, seed=11, **overrides):
+    from zett_b200 import synthetic
+    from zett_b200.modeling_hypernet import ZettHypernet, load_weights_numpy
+    cfg = synthetic.make_config(name, **overrides)
+    weights = synthetic.make_weights(cfg, seed=seed)
+    model = load_weights_numpy(ZettHypernet(cfg), weights).to("cuda")
+    return cfg, weights, model
+
+
+def test_golden_fixtures_through_public_api(torch_cuda, golden_dir):
+    """tests/golden/hypernet_*.npz were minted by the reference itself; the CUDA path must match them to 1e-3."""
+    import glob
+    torch = torch_cuda
+    from oracle import hypernet_oracle as ho
+    from zett_b200 import synthetic
+    for path in sorted(glob.glob(os.path.join(golden_dir, "hypernet_*.npz"))):
+        g = np.load(path)
+        meta = json.loads(str(g["meta"]))
+        cfg, weights, model = _model(torch, meta["config"], seed=meta["weight_seed"], **meta["overrides"])
+        src = synthetic.make_source_embeddings(cfg, seed=meta["source_seed"])
+        sf = g["surface_forms"]
+        lang = meta["lang_index"]
+        out = model(torch.from_numpy(sf).cuda(), source_embeddings=torch.from_numpy(src).cuda(),
+                    lang_index=None if lang is None else torch.tensor(lang))
+        masked = ho.fully_masked_rows(cfg, sf)
+        for name, got in zip(("pred_in", "pred_out", "pred_bias"), out):
+            if name not in g.files:
+                assert got is None or name == "pred_bias"
+                continue
+            fro, worst = ho.rel_errors(got.cpu().numpy(), g[name], exclude=masked)
+            assert fro < 1e-3 and worst < 1e-3, (path, name, fro, worst)
+
+
+def test_row_independence_and_idempotence(torch_cuda):
+    """Permutation / batch-composition invariance and run-to-run determinism, bit-exact."""
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    cfg, weights, model = _model(torch, "tiny")
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
+    sf = synthetic.make_random_surface_forms(cfg, 500, seed=3)
+    a = model(torch.from_numpy(sf).cuda(), source_embeddings=src)
+    b = model(torch.from_numpy(sf).cuda(), source_embeddings=src)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    perm = np.random.default_rng(0).permutation(len(sf))
+    c = model(torch.from_numpy(sf[perm][:123]).cuda(), source_embeddings=src)
+    for x, y in zip(a, c):
+        assert torch.equal(x[torch.from_numpy(perm[:123]).cuda()], y)
+    model.max_rows_per_pass = 64
+    model.refresh()
+    d = model(torch.from_numpy(sf).cuda(), source_embeddings=src)
+    for x, y in zip(a, d):
+        assert torch.equal(x, y)
+
+
+def test_out_of_range_id_raises(torch_cuda):
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    cfg, weights, model = _model(torch, "tiny")
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
+    sf = synthetic.make_random_surface_forms(cfg, 16, seed=3)
+    sf[7, 1] = cfg.original_vocab_size + cfg.hn_n_extra_tokens  # first id past the fallback table
+    with pytest.raises(IndexError):
+        model(torch.from_numpy(sf).cuda(), source_embeddings=src)
+    sf[7, 1] = -1
+    with pytest.raises(IndexError):
+        model(torch.from_numpy(sf).cuda(), source_embeddings=src)
+
+
+def test_unsupported_branches_raise(torch_cuda):
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    from zett_b200.modeling_hypernet import ZettHypernet
+    with pytest.raises(NotImplementedError):
+        ZettHypernet(synthetic.make_config("tiny", hn_add_inter_token_attention=True))
+    with pytest.raises(NotImplementedError):
+        ZettHypernet(synthetic.make_config("tiny", hn_model_type="t5"))
+    cfg, weights, model = _model(torch, "tiny")
+    sf = torch.zeros((2, 7), dtype=torch.int32).cuda()
+    with pytest.raises(NotImplementedError):
+        model(sf, target_priors=torch.zeros(2), source_embeddings=torch.zeros(300, 128).cuda())
+
+
+def test_end_to_end_tokens_to_embeddings(torch_cuda):
+    """token strings -> native retokenizer -> H2D -> forward -> D2H through transfer.make_predict / batched_inference,
+    against the oracle on the same surface forms; batched_inference == one-shot prediction."""
+    torch = torch_cuda
+    from oracle import hypernet_oracle as ho
+    from zett_b200 import synthetic
+    from zett_b200.surface_forms import get_surface_form_matrix
+    from zett_b200.transfer import batched_inference, default_args, make_predict
+    hn = synthetic.make_hn_tokenizer("unigram", 316, seed=5, pad_token="</s>")  # ids < tiny's V0 + n_extra = 316
+    tokens = synthetic.make_target_tokens(700, seed=6)
+    cfg, weights, model = _model(torch, "tiny", pad_token_id=int(hn.pad_token_id))
+    sf, n_trunc = get_surface_form_matrix(tokens, cfg.hn_surface_maxlen, hn)
+    assert sf.max() < cfg.original_vocab_size + cfg.hn_n_extra_tokens
+    src = synthetic.make_source_embeddings(cfg, seed=12)
+    predict = make_predict(model, src)
+    one = predict(sf)
+    want = ho.hypernet_forward(cfg, weights, sf, src)
+    masked = ho.fully_masked_rows(cfg, sf)
+    for g, w in zip(one, want):
+        fro, worst = ho.rel_errors(g, w, exclude=masked)
+        assert fro < 1e-3 and worst < 1e-3
+    cfg.hidden_size = cfg.n_embd
+    bi = batched_inference(sf, None, cfg, default_args(batch_size=256), predict, rng=np.random.default_rng(1))
+    for g, w in zip(bi, one):
+        np.testing.assert_array_equal(g, w)
+
+
+def test_full_vocab_properties_xlmr(torch_cuda):
+    """BASELINE config 2 at full size (50 257 rows, XLM-R shape): size-independent properties -- finite outputs,
+    duplicate surface-form rows give bit-identical predictions, pass-size invariance on a slice."""
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    cfg, weights, model = _model(torch, "xlmr")
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
+    sf = synthetic.make_random_surface_forms(cfg, 50257, seed=5)
+    sf[40000:40100] = sf[100:200]
+    out = model(torch.from_numpy(sf).cuda(), source_embeddings=src, lang_index=torch.tensor(3))
+    assert out[1] is None
+    assert torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+    assert torch.equal(out[0][40000:40100], out[0][100:200])
+    assert torch.equal(out[2][40000:40100], out[2][100:200])
+    st = model.native().stats()
+    assert st["rows"] == 50257 and st["kernel_launches"] > 0 and st["packed_positions"] > 0

@@ -70,3 +70,18 @@ def test_unsupported_branches_raise():
     cfg = synthetic.make_config("tiny", hn_model_type="t5")
     with pytest.raises(NotImplementedError):
         ho.hypernet_forward(cfg, {}, np.zeros((1, 7), np.int32), np.zeros((300, 128), np.float32))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_torch_oracle_matches_reference(golden_dir, case):
+    """The threaded torch-CPU restatement (bench.py's CPU baseline) against the same reference-minted goldens."""
+    import torch
+    from oracle import hypernet_oracle_torch as hot
+    g, meta, cfg, weights, src = load_case(golden_dir, case)
+    out = hot.hypernet_forward(cfg, hot.to_torch(weights), g["surface_forms"], torch.from_numpy(src),
+                               lang_index=meta["lang_index"])
+    for name, got in zip(("pred_in", "pred_out", "pred_bias"), out):
+        if name not in g.files:
+            continue
+        fro, worst = ho.rel_errors(got, g[name])
+        assert fro < 1e-5 and worst < 2e-5, (case, name, fro, worst)

@@ -8,7 +8,13 @@ Fields that training writes onto the config without declaring them (SURVEY.md se
 """
 from __future__ import annotations
 
+from typing import Dict, Tuple
+
 from transformers import PretrainedConfig
+
+# roberta-base constants that the reference pulls from the hub (hf_hypernet/modeling_hypernet.py:67-69)
+ROBERTA_MAX_POSITION_EMBEDDINGS = 514
+ROBERTA_LAYER_NORM_EPS = 1e-5
 
 # (field, default) in the reference's declaration order
 _HN_FIELDS = (
@@ -93,3 +99,64 @@ class ZettHypernetConfig(PretrainedConfig):
             f += n_layers * full_layer
         f += heads_out * (4 * H * I + 2 * H * d_out) + (2 * H if self.hn_predict_bias else 0)
         return float(f)
+
+
+def weight_shapes(cfg: "ZettHypernetConfig") -> Dict[str, Tuple[int, ...]]:
+    """The reference's ``state_dict`` names and shapes (hf_hypernet/modeling_hypernet.py:46-154)."""
+    H, I, D = cfg.hn_hidden_size, cfg.hn_intermediate_size, cfg.n_embd
+    E = cfg.n_in_embd
+    s: Dict[str, Tuple[int, ...]] = {}
+    s["model.embeddings.word_embeddings.weight"] = (cfg.pad_token_id + 1, H)
+    s["model.embeddings.token_type_embeddings.weight"] = (1, H)
+    s["model.embeddings.position_embeddings.weight"] = (ROBERTA_MAX_POSITION_EMBEDDINGS, H)
+    s["model.embeddings.LayerNorm.weight"] = (H,)
+    s["model.embeddings.LayerNorm.bias"] = (H,)
+    for l in range(cfg.hn_n_layers):
+        p = f"model.encoder.layer.{l}."
+        for n in ("query", "key", "value"):
+            s[p + f"attention.self.{n}.weight"] = (H, H)
+            s[p + f"attention.self.{n}.bias"] = (H,)
+        s[p + "attention.output.dense.weight"] = (H, H)
+        s[p + "attention.output.dense.bias"] = (H,)
+        s[p + "attention.output.LayerNorm.weight"] = (H,)
+        s[p + "attention.output.LayerNorm.bias"] = (H,)
+        s[p + "intermediate.dense.weight"] = (I, H)
+        s[p + "intermediate.dense.bias"] = (I,)
+        s[p + "output.dense.weight"] = (H, I)
+        s[p + "output.dense.bias"] = (H,)
+        s[p + "output.LayerNorm.weight"] = (H,)
+        s[p + "output.LayerNorm.bias"] = (H,)
+    s["fallback_embeddings.weight"] = (max(cfg.hn_n_extra_tokens, 1), E)
+    s["input_projection.0.weight"] = (H, E)
+    s["input_projection.0.bias"] = (H,)
+
+    def projector(prefix):
+        s[prefix + "dense1.weight"] = (I, H)
+        s[prefix + "dense1.bias"] = (I,)
+        s[prefix + "dense2.weight"] = (H, I)
+        s[prefix + "dense2.bias"] = (H,)
+        s[prefix + "ln.weight"] = (H,)
+        s[prefix + "ln.bias"] = (H,)
+
+    projector("input_projection.1.")
+    projector("output_projection.0.")
+    s["output_projection.1.weight"] = (E if cfg.hn_single_head else D, H)
+    s["output_projection.1.bias"] = (E if cfg.hn_single_head else D,)
+    if cfg.separate_out_embeddings and not cfg.hn_single_head:
+        projector("output_projection_out.0.")
+        s["output_projection_out.1.weight"] = (D, H)
+        s["output_projection_out.1.bias"] = (D,)
+    if cfg.hn_rescale_embeddings:
+        s["in_scaler.w"] = (1, E)
+        s["in_scaler.b"] = (1, E)
+        s["scaler.w"] = (1, D)
+        s["scaler.b"] = (1, D)
+        if cfg.separate_out_embeddings:
+            s["out_scaler.w"] = (1, D)
+            s["out_scaler.b"] = (1, D)
+    if cfg.hn_predict_bias:
+        s["bias_projection.weight"] = (1, H)
+        s["bias_projection.bias"] = (1,)
+    if cfg.hn_embed_lang_id:
+        s["lang_embeddings.weight"] = (cfg.n_langs, H)
+    return s

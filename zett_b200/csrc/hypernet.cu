@@ -1,0 +1,1026 @@
+// libzett_b200.so -- hypernetwork half of the C ABI declared in include/zett_b200.h.
+//
+// Host orchestration of the B200 forward of ZettHypernet.__call__ (reference hf_hypernet/modeling_hypernet.py:156-267):
+// weights are split once into 16-bit planes (zett_hn_finalize), a pass over <= max_rows_per_pass vocabulary rows is a
+// fixed sequence of kernels on the caller's stream -- pack, gather, tcgen05 GEMMs with fused bias / GELU / affine
+// epilogues, LayerNorm and short-sequence attention kernels -- with no host synchronisation: data-dependent sizes
+// (number of packed positions) stay on the device and the persistent GEMM kernels read them there.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/zett_b200.h"
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+using namespace zett;
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+#define ZETT_CUDA(expr)                                                                                      \
+  do {                                                                                                       \
+    cudaError_t e_ = (expr);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return fail(ZETT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+  } while (0)
+
+#define ZETT_TRY(expr)                \
+  do {                                \
+    int rc_ = (expr);                 \
+    if (rc_ != ZETT_OK) return rc_;   \
+  } while (0)
+
+// ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda) -----------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ZETT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) return fail(ZETT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return ZETT_OK;
+}
+
+// 3-D map {K, rows, planes} over 16-bit planes, box {64, box_rows, n_planes}, 128-byte swizzle, zero fill out of bounds
+int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long long k, long long plane_stride_elems,
+                    int box_rows, int n_planes, int split_fmt) {
+  EncodeTiledFn enc;
+  ZETT_TRY(get_encode_fn(&enc));
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(n_planes)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(k) * 2u, static_cast<cuuint64_t>(plane_stride_elems) * 2u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(n_planes)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (n_planes == 1) strides[1] = strides[0] * static_cast<cuuint64_t>(rows);
+  const CUtensorMapDataType dt = split_fmt == kFmtBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(map, dt, 3, const_cast<uint16_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%lld k=%lld plane_stride=%lld box_rows=%d planes=%d",
+             static_cast<int>(r), rows, k, plane_stride_elems, box_rows, n_planes);
+    return fail(ZETT_ERR_CUDA, buf);
+  }
+  return ZETT_OK;
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int num_sms = 0;
+  int cc_major = 0, cc_minor = 0;
+  bool attrs_set = false;
+};
+
+int query_device(DeviceInfo* d) {
+  ZETT_CUDA(cudaGetDevice(&d->device));
+  ZETT_CUDA(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, d->device));
+  ZETT_CUDA(cudaDeviceGetAttribute(&d->cc_major, cudaDevAttrComputeCapabilityMajor, d->device));
+  ZETT_CUDA(cudaDeviceGetAttribute(&d->cc_minor, cudaDevAttrComputeCapabilityMinor, d->device));
+  if (d->cc_major != 10)
+    return fail(ZETT_ERR_CUDA, "zett_b200 needs a Blackwell (sm_100a) GPU; found compute capability " +
+                                   std::to_string(d->cc_major) + "." + std::to_string(d->cc_minor));
+  return ZETT_OK;
+}
+
+constexpr int kMaxDynSmem = 232448;  // 227 KB
+constexpr int kGemmSmemSlack = 1024 /* alignment */ + 256 /* barriers + tmem slot */;
+
+unsigned long long* g_watchdog_host = nullptr;  // pinned, device-mapped; survives a trapped context
+
+std::string watchdog_text() {
+  char buf[160];
+  if (!g_watchdog_host) return "";
+  snprintf(buf, sizeof buf, " (watchdog code %llu block %llu aux %llu %llu)", g_watchdog_host[0], g_watchdog_host[1],
+           g_watchdog_host[2], g_watchdog_host[3]);
+  return buf;
+}
+
+int set_kernel_attrs(DeviceInfo* d) {
+  if (d->attrs_set) return ZETT_OK;
+  if (!g_watchdog_host) {
+    ZETT_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_watchdog_host), 4 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(g_watchdog_host, 0, 4 * sizeof(unsigned long long));
+  }
+  unsigned long long* dptr = nullptr;
+  ZETT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_watchdog_host, 0));
+  ZETT_CUDA(cudaMemcpyToSymbol(g_zett_watchdog, &dptr, sizeof dptr));
+  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  ZETT_CUDA(cudaFuncSetAttribute(gather_rescale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
+  d->attrs_set = true;
+  return ZETT_OK;
+}
+
+// ---- GEMM launcher ------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const uint16_t* a = nullptr;     // plane 0 of A, [a_rows, k]
+  long long a_rows = 0;            // rows the A buffer holds (TMA bound)
+  long long a_plane_stride = 0;    // elements between plane 0 and plane 1
+  const uint16_t* w = nullptr;     // plane 0 of W, [n, k]
+  long long w_plane_stride = 0;
+  int n = 0, k = 0;
+  int m_host = 0;
+  const int* m_dev = nullptr;
+  EpilogueParams ep{};
+};
+
+struct GemmEngine {
+  DeviceInfo dev;
+  int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 2-CTA, 3: SIMT
+  int n_terms = 3;
+  int split_fmt = kFmtBf16;
+  std::map<std::tuple<const void*, long long, long long, long long, int, int>, CUtensorMap> tmaps;
+  long long launches = 0;
+  // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
+  bool timing = false;
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
+
+  int time_mark(cudaStream_t stream) {
+    if (!timing) return ZETT_OK;
+    if (events_used == events.size()) {
+      cudaEvent_t e;
+      ZETT_CUDA(cudaEventCreate(&e));
+      events.push_back(e);
+    }
+    ZETT_CUDA(cudaEventRecord(events[events_used++], stream));
+    return ZETT_OK;
+  }
+  // after the stream has been synchronised
+  double collect_ms(long long* n_launches) {
+    double total = 0;
+    for (size_t i = 0; i + 1 < events_used; i += 2) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, events[i], events[i + 1]) == cudaSuccess) total += ms;
+    }
+    *n_launches = static_cast<long long>(events_used / 2);
+    events_used = 0;
+    return total;
+  }
+
+  int tmap(const uint16_t* base, long long rows, long long k, long long plane_stride, int box_rows, int n_planes,
+           const CUtensorMap** out) {
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows, n_planes);
+    auto it = tmaps.find(key);
+    if (it == tmaps.end()) {
+      CUtensorMap m;
+      ZETT_TRY(make_plane_tmap(&m, base, rows, k, plane_stride, box_rows, n_planes, split_fmt));
+      it = tmaps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return ZETT_OK;
+  }
+
+  static int pick_block_n(int n) {
+    for (int bn : {256, 128, 64, 32}) if (n % bn == 0) return bn;
+    return n >= 256 ? 256 : ((n + 31) / 32) * 32;
+  }
+
+  int launch(const GemmArgs& g, cudaStream_t stream) {
+    if (g.k % 8 != 0) return fail(ZETT_ERR_INVALID, "GEMM K must be a multiple of 8");
+    ++launches;
+    const int n_planes = n_terms == 3 ? 2 : 1;
+    if (impl == 3) {
+      SimtGemmParams s{};
+      s.a0 = g.a; s.a1 = n_planes == 2 ? g.a + g.a_plane_stride : nullptr;
+      s.w0 = g.w; s.w1 = n_planes == 2 ? g.w + g.w_plane_stride : nullptr;
+      s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k; s.split_fmt = split_fmt;
+      dim3 grid((g.n + 31) / 32, (g.m_host + 127) / 128);
+      if (grid.y == 0 || grid.x == 0) return ZETT_OK;
+      ZETT_TRY(time_mark(stream));
+      gemm_simt_kernel<<<grid, 128, 0, stream>>>(s, g.ep);
+      ZETT_CUDA(cudaGetLastError());
+      ZETT_TRY(time_mark(stream));
+      return ZETT_OK;
+    }
+    const int cg = impl == 1 ? 1 : 2;
+    GemmShape s{};
+    s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
+    s.block_n = pick_block_n(g.n);
+    s.n_terms = n_terms; s.n_planes = n_planes;
+    const int load_n = s.block_n / cg;
+    s.a_plane_bytes = kBlockM * kBlockK * 2;
+    s.b_plane_bytes = static_cast<uint32_t>(load_n) * kBlockK * 2;
+    s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes);
+    s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack) / static_cast<int>(s.stage_bytes));
+    if (s.num_stages < 2) return fail(ZETT_ERR_INVALID, "GEMM tile does not fit two pipeline stages");
+    // instruction descriptor (kind::f16): D fp32, A/B bf16|fp16, both K-major, N >> 3, M >> 4
+    const uint32_t fmt = split_fmt == kFmtBf16 ? 1u : 0u;
+    s.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(s.block_n >> 3) << 17) |
+              (static_cast<uint32_t>((kBlockM * cg) >> 4) << 24);
+    const CUtensorMap *ta, *tb;
+    ZETT_TRY(tmap(g.a, g.a_rows, g.k, g.a_plane_stride, kBlockM, n_planes, &ta));
+    ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n, n_planes, &tb));
+    const int tile_m = kBlockM * cg;
+    const long long m_tiles = (g.m_host + tile_m - 1) / tile_m;
+    const long long n_tiles = (g.n + s.block_n - 1) / s.block_n;
+    const long long tiles = m_tiles * n_tiles;
+    if (tiles == 0) return ZETT_OK;
+    int ctas = static_cast<int>(std::min<long long>(dev.num_sms / cg, tiles)) * cg;
+    const size_t smem = static_cast<size_t>(s.num_stages) * s.stage_bytes + kGemmSmemSlack;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ZETT_TRY(time_mark(stream));
+    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, *ta, *tb, s, g.ep));
+    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, *ta, *tb, s, g.ep));
+    ZETT_TRY(time_mark(stream));
+    return ZETT_OK;
+  }
+};
+
+// ---- small helpers ------------------------------------------------------------------------------------------------
+__global__ void convert_to_f32_kernel(const uint16_t* x, long long n, float* y, int dtype) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = dtype == ZETT_BF16 ? __bfloat162float(__ushort_as_bfloat16(x[i])) : __half2float(__ushort_as_half(x[i]));
+}
+
+// lang_pre[l] = lang_embeddings[l] - (token_type_embeddings[0] + position_embeddings[L])   (modeling_hypernet.py:194-199)
+__global__ void lang_pre_kernel(const float* lang, const float* type0, const float* posL, long long n_langs, int H, float* out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_langs * H;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % H);
+    out[i] = __fsub_rn(lang[i], __fadd_rn(type0[c], posL[c]));
+  }
+}
+
+__global__ void fill_f32_kernel(float* x, long long n, long long ld, float v) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    x[i * ld] = v;
+}
+
+struct Staged {
+  float* dev = nullptr;
+  std::vector<int64_t> shape;
+  long long numel() const {
+    long long n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct LinearW {
+  uint16_t* planes = nullptr;  // [2, n, k]
+  float* bias = nullptr;       // [n]
+  int n = 0, k = 0;
+  long long plane_stride() const { return static_cast<long long>(n) * k; }
+};
+
+struct Projector {  // ProjectorBlock
+  LinearW dense1, dense2;
+  float *ln_w = nullptr, *ln_b = nullptr;
+};
+
+struct EncoderLayer {
+  LinearW qkv, attn_out, inter, out;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+};
+
+struct Workspace {
+  long long rows_cap = 0;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  // pack metadata
+  int *counts_all = nullptr, *row_start1 = nullptr, *row_start2 = nullptr, *tok_src = nullptr, *tok_pos = nullptr,
+      *tok_enc = nullptr, *tok1_row = nullptr, *lang_enc = nullptr, *tok2_row = nullptr;
+  unsigned char* tok2_valid = nullptr;
+  // position-indexed buffers
+  uint16_t *P_E = nullptr, *PH_a = nullptr, *PH_b = nullptr, *PI = nullptr;
+  float *F1 = nullptr, *F2 = nullptr, *F3 = nullptr, *F4 = nullptr;
+  // row-indexed (compact) buffers
+  float *CX0 = nullptr, *CQ0 = nullptr, *CZ = nullptr, *CX1 = nullptr, *CH0 = nullptr;
+  uint16_t *CPX0 = nullptr, *CPC = nullptr, *CPX1 = nullptr, *CPH0 = nullptr, *CPG = nullptr;
+};
+
+constexpr int kMaxPassSlots = 4096;
+
+}  // namespace
+
+struct zett_hn {
+  zett_hn_config cfg{};
+  int L = 0, S = 0, H = 0, I = 0, D = 0, E = 0, heads = 0, dh = 0, n_fallback = 1;
+  bool finalized = false;
+  GemmEngine gemm;
+  std::unordered_map<std::string, Staged> staged;
+  std::vector<void*> owned;  // device allocations that live as long as the handle
+  // finalized weights
+  LinearW in_proj0;
+  Projector in_proj1, head_in, head_out;
+  LinearW out_in, out_out;  // final H -> D projections (single_head: two row slices of one weight)
+  std::vector<EncoderLayer> layers;
+  float *fallback = nullptr, *in_scale_w = nullptr, *in_scale_b = nullptr, *scale_w = nullptr, *scale_b = nullptr,
+        *oscale_w = nullptr, *oscale_b = nullptr, *type0 = nullptr, *pos_table = nullptr, *emb_ln_w = nullptr,
+        *emb_ln_b = nullptr, *lang_pre = nullptr, *biasproj_w = nullptr, *biasproj_b = nullptr;
+  Workspace ws;
+  // statistics
+  long long passes = 0;
+  zett_hn_stats stats{};
+  double coef_t1 = 0, coef_t2 = 0, coef_rows = 0;  // FLOPs per surface position / encoder position / row
+};
+
+namespace {
+
+int dev_alloc(zett_hn* h, void** p, size_t bytes, bool workspace) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  ZETT_CUDA(cudaMalloc(p, bytes));
+  if (workspace) {
+    h->ws.allocs.push_back(*p);
+    h->ws.bytes += bytes;
+  } else {
+    h->owned.push_back(*p);
+  }
+  return ZETT_OK;
+}
+
+void free_workspace(zett_hn* h) {
+  for (void* p : h->ws.allocs) cudaFree(p);
+  h->ws = Workspace{};
+  h->gemm.tmaps.clear();
+}
+
+size_t workspace_bytes_for(const zett_hn* h, long long rows) {
+  const long long t1 = rows * h->L, t2 = rows * h->S;
+  const long long H = h->H, I = h->I, E = h->E;
+  size_t b = 0;
+  b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 4 * t1 + rows + t2) + t2;
+  b += 2ull * 2 * t1 * E;                 // P_E
+  b += 2ull * 2 * t2 * H * 2;             // PH_a, PH_b
+  b += 2ull * 2 * t2 * I;                 // PI
+  b += 4ull * t2 * H * 3 + 4ull * t2 * 3 * H;  // F1..F3, F4
+  b += 4ull * rows * H * 5 + 2ull * 2 * rows * H * 4 + 2ull * 2 * rows * I;
+  return b + 64 * 256;
+}
+
+int ensure_workspace(zett_hn* h, long long rows) {
+  if (h->ws.rows_cap >= rows) return ZETT_OK;
+  free_workspace(h);
+  Workspace& w = h->ws;
+  const long long t1 = rows * h->L, t2 = rows * h->S;
+  const long long H = h->H, I = h->I, E = h->E;
+#define WS_ALLOC(ptr, count) ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&(ptr)), sizeof(*(ptr)) * static_cast<size_t>(count), true))
+  WS_ALLOC(w.counts_all, kMaxPassSlots * kCntSlots);
+  WS_ALLOC(w.row_start1, rows + 1);
+  WS_ALLOC(w.row_start2, rows + 1);
+  WS_ALLOC(w.tok_src, t1);
+  WS_ALLOC(w.tok_pos, t1);
+  WS_ALLOC(w.tok_enc, t1);
+  WS_ALLOC(w.tok1_row, t1);
+  WS_ALLOC(w.lang_enc, rows);
+  WS_ALLOC(w.tok2_row, t2);
+  WS_ALLOC(w.tok2_valid, t2);
+  WS_ALLOC(w.P_E, 2 * t1 * E);
+  WS_ALLOC(w.PH_a, 2 * t2 * H);
+  WS_ALLOC(w.PH_b, 2 * t2 * H);
+  WS_ALLOC(w.PI, 2 * t2 * I);
+  WS_ALLOC(w.F1, t2 * H);
+  WS_ALLOC(w.F2, t2 * H);
+  WS_ALLOC(w.F3, t2 * H);
+  WS_ALLOC(w.F4, t2 * 3 * H);
+  WS_ALLOC(w.CX0, rows * H);
+  WS_ALLOC(w.CQ0, rows * H);
+  WS_ALLOC(w.CZ, rows * H);
+  WS_ALLOC(w.CX1, rows * H);
+  WS_ALLOC(w.CH0, rows * H);
+  WS_ALLOC(w.CPX0, 2 * rows * H);
+  WS_ALLOC(w.CPC, 2 * rows * H);
+  WS_ALLOC(w.CPX1, 2 * rows * H);
+  WS_ALLOC(w.CPH0, 2 * rows * H);
+  WS_ALLOC(w.CPG, 2 * rows * I);
+#undef WS_ALLOC
+  ZETT_CUDA(cudaMemset(w.counts_all, 0, sizeof(int) * kMaxPassSlots * kCntSlots));
+  w.rows_cap = rows;
+  return ZETT_OK;
+}
+
+int staged_get(zett_hn* h, const std::string& name, std::vector<int64_t> shape, float** out) {
+  auto it = h->staged.find(name);
+  if (it == h->staged.end()) return fail(ZETT_ERR_STATE, "missing weight: " + name);
+  if (it->second.shape != shape) {
+    std::string got, want;
+    for (auto s : it->second.shape) got += std::to_string(s) + ",";
+    for (auto s : shape) want += std::to_string(s) + ",";
+    return fail(ZETT_ERR_INVALID, "weight " + name + " has shape [" + got + "] expected [" + want + "]");
+  }
+  *out = it->second.dev;
+  return ZETT_OK;
+}
+
+// keep a small fp32 tensor for the lifetime of the handle
+int take_vector(zett_hn* h, const std::string& name, std::vector<int64_t> shape, float** out) {
+  ZETT_TRY(staged_get(h, name, shape, out));
+  h->owned.push_back(*out);
+  h->staged.erase(name);
+  return ZETT_OK;
+}
+
+int split_into(zett_hn* h, const float* src, long long rows, long long k, uint16_t* p0, long long plane_stride) {
+  const long long n4 = rows * k / 4;
+  const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8));
+  split_planes_kernel<<<std::max(blocks, 1), 256>>>(src, n4, p0, h->gemm.n_terms == 3 ? p0 + plane_stride : nullptr,
+                                                    h->gemm.split_fmt);
+  ZETT_CUDA(cudaGetLastError());
+  return ZETT_OK;
+}
+
+// Linear from one or several stacked reference weights (stacking fuses query/key/value into one GEMM)
+int make_linear(zett_hn* h, const std::vector<std::string>& prefixes, int n_each, int k, LinearW* out) {
+  const int parts = static_cast<int>(prefixes.size());
+  out->n = n_each * parts;
+  out->k = k;
+  if ((static_cast<long long>(n_each) * k) % 4 != 0) return fail(ZETT_ERR_INVALID, "Linear size must be a multiple of 4");
+  ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&out->planes), sizeof(uint16_t) * 2ull * out->n * k, false));
+  ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&out->bias), sizeof(float) * out->n, false));
+  for (int i = 0; i < parts; ++i) {
+    float *w, *b;
+    ZETT_TRY(staged_get(h, prefixes[i] + ".weight", {n_each, k}, &w));
+    ZETT_TRY(staged_get(h, prefixes[i] + ".bias", {n_each}, &b));
+    ZETT_TRY(split_into(h, w, n_each, k, out->planes + static_cast<long long>(i) * n_each * k, out->plane_stride()));
+    ZETT_CUDA(cudaMemcpy(out->bias + static_cast<long long>(i) * n_each, b, sizeof(float) * n_each, cudaMemcpyDeviceToDevice));
+  }
+  ZETT_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < parts; ++i) {
+    for (const char* leaf : {".weight", ".bias"}) {
+      auto it = h->staged.find(prefixes[i] + leaf);
+      cudaFree(it->second.dev);
+      h->staged.erase(it);
+    }
+  }
+  return ZETT_OK;
+}
+
+int make_projector(zett_hn* h, const std::string& prefix, Projector* p) {
+  ZETT_TRY(make_linear(h, {prefix + "dense1"}, h->I, h->H, &p->dense1));
+  ZETT_TRY(make_linear(h, {prefix + "dense2"}, h->H, h->I, &p->dense2));
+  ZETT_TRY(take_vector(h, prefix + "ln.weight", {h->H}, &p->ln_w));
+  ZETT_TRY(take_vector(h, prefix + "ln.bias", {h->H}, &p->ln_b));
+  return ZETT_OK;
+}
+
+uint16_t* plane1(uint16_t* p0, long long stride, const zett_hn* h) { return h->gemm.n_terms == 3 ? p0 + stride : nullptr; }
+
+int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
+  if (max_rows <= 0) return ZETT_OK;
+  p.H = h->H;
+  p.split_fmt = h->gemm.split_fmt;
+  const int h4 = h->H / 4;
+  int threads = std::min(256, std::max(32, ((h4 + 31) / 32) * 32));
+  const int grid = static_cast<int>(std::min<long long>(max_rows, 148LL * 16));
+  layernorm_kernel<<<grid, threads, 0, stream>>>(p);
+  ZETT_CUDA(cudaGetLastError());
+  ++h->gemm.launches;
+  return ZETT_OK;
+}
+
+int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
+  const long long warps = static_cast<long long>(p.n_rows) * p.n_heads;
+  if (warps == 0) return ZETT_OK;
+  const int grid = static_cast<int>((warps + 7) / 8);
+  switch (h->dh / 32) {
+    case 1: attention_kernel<1><<<grid, 256, 0, stream>>>(p); break;
+    case 2: attention_kernel<2><<<grid, 256, 0, stream>>>(p); break;
+    case 4: attention_kernel<4><<<grid, 256, 0, stream>>>(p); break;
+    case 8: attention_kernel<8><<<grid, 256, 0, stream>>>(p); break;
+    default: return fail(ZETT_ERR_UNSUPPORTED, "attention head size must be 32, 64, 128 or 256");
+  }
+  ZETT_CUDA(cudaGetLastError());
+  ++h->gemm.launches;
+  return ZETT_OK;
+}
+
+enum MClass { kMSurface, kMEncoder, kMRows };
+
+// One Linear layer through the GEMM engine.  `a` / `out_*` are plane-0 pointers; `cap` = rows the buffers hold.
+int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const uint16_t* a, long long cap, MClass mclass,
+               int m_rows, const int* counts, int act, float* out_f32, long long ld_f32, uint16_t* out_p0,
+               long long out_cap, const float* col_scale, const float* col_shift, cudaStream_t stream) {
+  GemmArgs g;
+  g.a = a; g.a_rows = cap; g.a_plane_stride = cap * w.k;
+  g.w = w.planes + static_cast<long long>(row_off) * w.k; g.w_plane_stride = w.plane_stride();
+  g.n = n_rows_w; g.k = w.k;
+  if (mclass == kMRows) { g.m_host = m_rows; g.m_dev = nullptr; }
+  else { g.m_host = static_cast<int>(cap); g.m_dev = counts + (mclass == kMSurface ? kCntSurface : kCntEncoder); }
+  g.ep.bias = w.bias + row_off;
+  g.ep.act = act;
+  g.ep.col_scale = col_scale; g.ep.col_shift = col_shift;
+  g.ep.out_f32 = out_f32; g.ep.ld_out = ld_f32;
+  g.ep.out_p0 = out_p0; g.ep.out_p1 = out_p0 ? plane1(out_p0, out_cap * n_rows_w, h) : nullptr; g.ep.ld_split = n_rows_w;
+  g.ep.split_fmt = h->gemm.split_fmt;
+  const double f = 2.0 * n_rows_w * w.k;
+  if (mclass == kMSurface) h->coef_t1 += f; else if (mclass == kMEncoder) h->coef_t2 += f; else h->coef_rows += f;
+  return h->gemm.launch(g, stream);
+}
+
+// ProjectorBlock + LayerNorm(h + x) on `cap`-row buffers: x (fp32 xf, planes xp) -> planes/f32 out
+int run_projector(zett_hn* h, const Projector& pb, const uint16_t* xp, const float* xf, long long cap, MClass mclass,
+                  int m_rows, const int* counts, uint16_t* pg, float* z, LnParams ln_out, cudaStream_t stream) {
+  ZETT_TRY(run_linear(h, pb.dense1, 0, h->I, xp, cap, mclass, m_rows, counts, kActGeluTanh, nullptr, 0, pg, cap, nullptr,
+                      nullptr, stream));
+  ZETT_TRY(run_linear(h, pb.dense2, 0, h->H, pg, cap, mclass, m_rows, counts, kActGeluTanh, z, h->H, nullptr, 0, nullptr,
+                      nullptr, stream));
+  ln_out.a = z; ln_out.lda = h->H; ln_out.res = xf;
+  ln_out.gamma = pb.ln_w; ln_out.beta = pb.ln_b; ln_out.eps = 1e-6f;
+  if (mclass == kMRows) { ln_out.n_dev = nullptr; ln_out.n_host = m_rows; }
+  else { ln_out.n_dev = counts + (mclass == kMSurface ? kCntSurface : kCntEncoder); ln_out.n_host = 0; }
+  return launch_ln(h, ln_out, mclass == kMRows ? m_rows : cap, stream);
+}
+
+int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, long long v0_rows, int lang_index,
+                 float* pred_in, float* pred_out, float* pred_bias, long long ld_pred, long long ld_bias,
+                 cudaStream_t stream) {
+  Workspace& w = h->ws;
+  const int H = h->H, I = h->I, D = h->D, E = h->E, L = h->L, S = h->S;
+  const long long cap1 = w.rows_cap * L, cap2 = w.rows_cap * S, capr = w.rows_cap;
+  const bool lang = h->cfg.hn_embed_lang_id != 0;
+  const int n_layers = h->cfg.hn_n_layers;
+  int* counts = w.counts_all + (h->passes % kMaxPassSlots) * kCntSlots;
+  const int fmt = h->gemm.split_fmt;
+  h->coef_t1 = h->coef_t2 = h->coef_rows = 0;
+
+  // ---- pack ------------------------------------------------------------------------------------------------------
+  ZETT_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * kCntSlots, stream));
+  PackParams pp{};
+  pp.ids = ids; pp.n_rows = rows; pp.L = L; pp.pad_id = h->cfg.pad_token_id; pp.v0 = h->cfg.original_vocab_size;
+  pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.counts = counts;
+  pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_src = w.tok_src; pp.tok_pos = w.tok_pos;
+  pp.tok_enc = w.tok_enc; pp.tok1_row = w.tok1_row; pp.lang_enc = w.lang_enc; pp.tok2_row = w.tok2_row; pp.tok2_valid = w.tok2_valid;
+  pack_rows_kernel<<<1, kPackThreads, 0, stream>>>(pp);
+  ZETT_CUDA(cudaGetLastError());
+  ++h->gemm.launches;
+
+  // ---- gather + in_scaler + split  (modeling_hypernet.py:170-188) ------------------------------------------------
+  {
+    GatherParams gp{};
+    gp.source = source; gp.v0_rows = v0_rows; gp.fallback = h->fallback;
+    gp.scale_w = h->in_scale_w; gp.scale_b = h->in_scale_b; gp.tok_src = w.tok_src; gp.n_tok = counts + kCntSurface;
+    gp.E = E; gp.split_fmt = fmt; gp.out_p0 = w.P_E; gp.out_p1 = plane1(w.P_E, cap1 * E, h);
+    const size_t smem = 2ull * E * 4;
+    const int per_sm = std::max<int>(1, std::min<int>(8, 200 * 1024 / static_cast<int>(smem + 64)));
+    const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(rows) * L, 148LL * per_sm));
+    gather_rescale_kernel<<<grid, kGatherThreads, smem, stream>>>(gp);
+    ZETT_CUDA(cudaGetLastError());
+    ++h->gemm.launches;
+  }
+
+  // ---- input_projection = Linear(E, H); ProjectorBlock  (modeling_hypernet.py:100-110,189) -----------------------
+  ZETT_TRY(run_linear(h, h->in_proj0, 0, H, w.P_E, cap1, kMSurface, 0, counts, kActNone, w.F1, H, w.PH_a, cap1, nullptr,
+                      nullptr, stream));
+  {
+    LnParams ln{};  // U = LN_1e-6(gelu(dense2(gelu(dense1 y))) + y), in place over Z
+    ln.out_f32 = w.F2;
+    ZETT_TRY(run_projector(h, h->in_proj1, w.PH_a, w.F1, cap1, kMSurface, 0, counts, w.PI, w.F2, ln, stream));
+  }
+  // ---- RobertaEmbeddings: + token_type[0] + position[pos]; LayerNorm 1e-5; scatter into the encoder packing -------
+  const bool single_layer = n_layers == 1;
+  {
+    LnParams ln{};
+    ln.a = w.F2; ln.lda = H; ln.vec0 = h->type0; ln.table = h->pos_table; ln.table_idx = w.tok_pos;
+    ln.gamma = h->emb_ln_w; ln.beta = h->emb_ln_b; ln.eps = h->cfg.encoder_layer_norm_eps;
+    ln.n_dev = counts + kCntSurface; ln.out_index = w.tok_enc;
+    ln.out_f32 = w.F3; ln.out_p0 = w.PH_a; ln.out_p1 = plane1(w.PH_a, cap2 * H, h);
+    if (single_layer) {
+      ln.tok_row = w.tok1_row; ln.row_start = w.row_start1;
+      ln.c_f32 = w.CX0; ln.c_p0 = w.CPX0; ln.c_p1 = plane1(w.CPX0, capr * H, h);
+    }
+    ZETT_TRY(launch_ln(h, ln, cap1, stream));
+    if (lang) {  // lang-id slot: lang_embedding (position/type pre-subtracted) at position L  (modeling_hypernet.py:192-218)
+      LnParams ll{};
+      ll.a = h->lang_pre + static_cast<long long>(lang_index) * H; ll.lda = 0; ll.vec0 = h->type0;
+      ll.table = h->pos_table; ll.table_idx = nullptr; ll.table_const = L;
+      ll.gamma = h->emb_ln_w; ll.beta = h->emb_ln_b; ll.eps = h->cfg.encoder_layer_norm_eps;
+      ll.n_host = rows; ll.out_index = w.lang_enc;
+      ll.out_f32 = w.F3; ll.out_p0 = w.PH_a; ll.out_p1 = plane1(w.PH_a, cap2 * H, h);
+      ZETT_TRY(launch_ln(h, ll, rows, stream));
+    }
+  }
+
+  // ---- encoder layers (post-LN RoBERTa); the last one is pruned to the position-0 query -------------------------
+  const float scale = 1.0f / sqrtf(static_cast<float>(h->dh));
+  for (int l = 0; l < n_layers; ++l) {
+    const EncoderLayer& ly = h->layers[l];
+    const bool last = l == n_layers - 1;
+    if (!last) {
+      ZETT_TRY(run_linear(h, ly.qkv, 0, 3 * H, w.PH_a, cap2, kMEncoder, 0, counts, kActNone, w.F4, 3 * H, nullptr, 0,
+                          nullptr, nullptr, stream));
+      AttnParams ap{};
+      ap.q = w.F4; ap.ldq = 3 * H; ap.k = w.F4 + H; ap.ldk = 3 * H; ap.v = w.F4 + 2 * H; ap.ldv = 3 * H;
+      ap.row_start = w.row_start2; ap.valid = w.tok2_valid; ap.n_rows = rows; ap.n_heads = h->heads; ap.dh = h->dh;
+      ap.scale = scale; ap.row0_only = 0; ap.out_p0 = w.PH_b; ap.out_p1 = plane1(w.PH_b, cap2 * H, h); ap.ld_out = H;
+      ap.split_fmt = fmt;
+      ZETT_TRY(launch_attention(h, ap, stream));
+      ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.PH_b, cap2, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, 0, nullptr,
+                          nullptr, stream));
+      LnParams l1{};
+      l1.a = w.F2; l1.lda = H; l1.res = w.F3; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
+      l1.n_dev = counts + kCntEncoder; l1.out_f32 = w.F1; l1.out_p0 = w.PH_b; l1.out_p1 = plane1(w.PH_b, cap2 * H, h);
+      ZETT_TRY(launch_ln(h, l1, cap2, stream));
+      ZETT_TRY(run_linear(h, ly.inter, 0, I, w.PH_b, cap2, kMEncoder, 0, counts, kActGeluErf, nullptr, 0, w.PI, cap2, nullptr,
+                          nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.out, 0, H, w.PI, cap2, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, 0, nullptr, nullptr,
+                          stream));
+      LnParams l2{};
+      l2.a = w.F2; l2.lda = H; l2.res = w.F1; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
+      l2.n_dev = counts + kCntEncoder; l2.out_f32 = w.F3; l2.out_p0 = w.PH_a; l2.out_p1 = plane1(w.PH_a, cap2 * H, h);
+      if (l == n_layers - 2) {  // the pruned last layer reads position 0 of every row from compact buffers
+        l2.tok_row = w.tok2_row; l2.row_start = w.row_start2;
+        l2.c_f32 = w.CX0; l2.c_p0 = w.CPX0; l2.c_p1 = plane1(w.CPX0, capr * H, h);
+      }
+      ZETT_TRY(launch_ln(h, l2, cap2, stream));
+    } else {
+      // K, V for every position; Q, attention output, MLP only for position 0 of each row (hidden[:, 0], :231-234)
+      ZETT_TRY(run_linear(h, ly.qkv, H, 2 * H, w.PH_a, cap2, kMEncoder, 0, counts, kActNone, w.F4, 2 * H, nullptr, 0, nullptr,
+                          nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.qkv, 0, H, w.CPX0, capr, kMRows, rows, counts, kActNone, w.CQ0, H, nullptr, 0, nullptr,
+                          nullptr, stream));
+      AttnParams ap{};
+      ap.q = w.CQ0; ap.ldq = H; ap.k = w.F4; ap.ldk = 2 * H; ap.v = w.F4 + H; ap.ldv = 2 * H;
+      ap.row_start = w.row_start2; ap.valid = w.tok2_valid; ap.n_rows = rows; ap.n_heads = h->heads; ap.dh = h->dh;
+      ap.scale = scale; ap.row0_only = 1; ap.out_p0 = w.CPC; ap.out_p1 = plane1(w.CPC, capr * H, h); ap.ld_out = H;
+      ap.split_fmt = fmt;
+      ZETT_TRY(launch_attention(h, ap, stream));
+      ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.CPC, capr, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, 0, nullptr,
+                          nullptr, stream));
+      LnParams l1{};
+      l1.a = w.CZ; l1.lda = H; l1.res = w.CX0; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
+      l1.n_host = rows; l1.out_f32 = w.CX1; l1.out_p0 = w.CPX1; l1.out_p1 = plane1(w.CPX1, capr * H, h);
+      ZETT_TRY(launch_ln(h, l1, rows, stream));
+      ZETT_TRY(run_linear(h, ly.inter, 0, I, w.CPX1, capr, kMRows, rows, counts, kActGeluErf, nullptr, 0, w.CPG, capr, nullptr,
+                          nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.out, 0, H, w.CPG, capr, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, 0, nullptr, nullptr,
+                          stream));
+      LnParams l2{};
+      l2.a = w.CZ; l2.lda = H; l2.res = w.CX1; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
+      l2.n_host = rows; l2.out_f32 = w.CH0; l2.out_p0 = w.CPH0; l2.out_p1 = plane1(w.CPH0, capr * H, h);
+      if (h->cfg.hn_predict_bias) {  // bias_projection(hidden[:, 0])[..., 0]  (:260-261)
+        l2.dot_w = h->biasproj_w; l2.dot_b = h->biasproj_b; l2.dot_out = pred_bias; l2.dot_ld = ld_bias;
+      }
+      ZETT_TRY(launch_ln(h, l2, rows, stream));
+    }
+  }
+  if (!h->cfg.hn_predict_bias) {  // zeros  (:262-265)
+    fill_f32_kernel<<<std::max(1, std::min(1184, (rows + 255) / 256)), 256, 0, stream>>>(pred_bias, rows, ld_bias, 0.f);
+    ZETT_CUDA(cudaGetLastError());
+    ++h->gemm.launches;
+  }
+
+  // ---- output heads: ProjectorBlock + Linear(H, D) + Rescaler  (modeling_hypernet.py:112-144,236-258) ------------
+  auto run_head = [&](const Projector& pb, const LinearW& proj_in, int off_in, float* dst_in, const float* sw_in,
+                      const float* sb_in, const LinearW* proj_out, int off_out, float* dst_out, const float* sw_out,
+                      const float* sb_out) -> int {
+    LnParams ln{};
+    ln.out_p0 = w.CPX1; ln.out_p1 = plane1(w.CPX1, capr * H, h);
+    ZETT_TRY(run_projector(h, pb, w.CPH0, w.CH0, capr, kMRows, rows, counts, w.CPG, w.CZ, ln, stream));
+    ZETT_TRY(run_linear(h, proj_in, off_in, D, w.CPX1, capr, kMRows, rows, counts, kActNone, dst_in, ld_pred, nullptr, 0, sw_in,
+                        sb_in, stream));
+    if (proj_out)
+      ZETT_TRY(run_linear(h, *proj_out, off_out, D, w.CPX1, capr, kMRows, rows, counts, kActNone, dst_out, ld_pred, nullptr, 0,
+                          sw_out, sb_out, stream));
+    return ZETT_OK;
+  };
+  const bool separate = h->cfg.separate_out_embeddings != 0;
+  if (h->cfg.hn_single_head) {
+    ZETT_TRY(run_head(h->head_in, h->out_in, 0, pred_in, h->scale_w, h->scale_b, separate ? &h->out_in : nullptr, D, pred_out,
+                      h->oscale_w, h->oscale_b));
+  } else {
+    ZETT_TRY(run_head(h->head_in, h->out_in, 0, pred_in, h->scale_w, h->scale_b, nullptr, 0, nullptr, nullptr, nullptr));
+    if (separate)
+      ZETT_TRY(run_head(h->head_out, h->out_out, 0, pred_out, h->oscale_w, h->oscale_b, nullptr, 0, nullptr, nullptr, nullptr));
+  }
+  ++h->passes;
+  return ZETT_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+const char* zett_last_error(void) { return g_error.c_str(); }
+void zett_set_last_error_(const char* msg) { g_error = msg ? msg : ""; }
+int zett_abi_version(void) { return ZETT_B200_ABI_VERSION; }
+
+int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
+  if (!cfg || !out) return fail(ZETT_ERR_INVALID, "null argument");
+  if (cfg->struct_bytes != static_cast<int32_t>(sizeof(zett_hn_config)))
+    return fail(ZETT_ERR_INVALID, "zett_hn_config size mismatch (ABI)");
+  // the branches the reference rejects (modeling_hypernet.py:78-79, 85-89, 164-168) and the shape-inconsistent one
+  if (!cfg->hn_model_type_is_roberta) return fail(ZETT_ERR_UNSUPPORTED, "hn_model_type != 'roberta'");
+  if (cfg->hn_add_inter_token_attention || cfg->hn_embed_target_priors)
+    return fail(ZETT_ERR_UNSUPPORTED, "hn_add_inter_token_attention / hn_embed_target_priors");
+  if (!cfg->hn_embed_using_source_embeddings) return fail(ZETT_ERR_UNSUPPORTED, "hn_embed_using_source_embeddings must be set");
+  if (cfg->hn_concat_last_hidden_state) return fail(ZETT_ERR_UNSUPPORTED, "hn_concat_last_hidden_state");
+  const int H = cfg->hn_hidden_size, I = cfg->hn_intermediate_size, D = cfg->n_embd;
+  if (H <= 0 || I <= 0 || D <= 0 || cfg->hn_n_layers < 1) return fail(ZETT_ERR_INVALID, "hidden sizes / layer count must be positive");
+  if (cfg->hn_surface_maxlen < 1 || cfg->hn_surface_maxlen > kMaxSurfaceLen - 1)
+    return fail(ZETT_ERR_INVALID, "hn_surface_maxlen must be in [1, 31]");
+  if (H % 8 || I % 8 || D % 8) return fail(ZETT_ERR_INVALID, "n_embd, hn_hidden_size, hn_intermediate_size must be multiples of 8");
+  if (H / 4 > kLnMaxVec * 256) return fail(ZETT_ERR_INVALID, "hn_hidden_size too large for the LayerNorm kernel (max 8192)");
+  const int heads = cfg->hn_num_attention_heads > 0 ? cfg->hn_num_attention_heads : H / 64;
+  if (heads <= 0 || H % heads) return fail(ZETT_ERR_INVALID, "hn_hidden_size must be divisible by the number of heads");
+  const int dh = H / heads;
+  if (dh != 32 && dh != 64 && dh != 128 && dh != 256) return fail(ZETT_ERR_UNSUPPORTED, "attention head size must be 32, 64, 128 or 256");
+  if (cfg->hn_embed_lang_id && cfg->n_langs <= 0) return fail(ZETT_ERR_INVALID, "hn_embed_lang_id needs n_langs");
+  if (cfg->original_vocab_size <= 0) return fail(ZETT_ERR_INVALID, "original_vocab_size must be set");
+  if (cfg->max_position_embeddings < cfg->hn_surface_maxlen + 1) return fail(ZETT_ERR_INVALID, "max_position_embeddings too small");
+  if ((cfg->separate_out_embeddings ? 2 : 1) * D > 16384) return fail(ZETT_ERR_INVALID, "source embedding rows wider than 16384 floats are not supported");
+
+  auto* h = new zett_hn();
+  h->cfg = *cfg;
+  h->L = cfg->hn_surface_maxlen;
+  h->S = h->L + (cfg->hn_embed_lang_id ? 1 : 0);
+  h->H = H; h->I = I; h->D = D;
+  h->E = cfg->separate_out_embeddings ? 2 * D : D;
+  h->heads = heads; h->dh = dh;
+  h->n_fallback = std::max(cfg->hn_n_extra_tokens, 1);
+  if (h->cfg.max_rows_per_pass <= 0) h->cfg.max_rows_per_pass = 16384;
+  if (h->cfg.encoder_layer_norm_eps <= 0.f) h->cfg.encoder_layer_norm_eps = 1e-5f;
+  int rc = query_device(&h->gemm.dev);
+  if (rc == ZETT_OK) rc = set_kernel_attrs(&h->gemm.dev);
+  if (rc != ZETT_OK) { delete h; return rc; }
+  int impl = cfg->gemm_impl;
+  if (const char* e = getenv("ZETT_GEMM_IMPL")) impl = atoi(e);
+  h->gemm.impl = impl == 0 ? 2 : impl;
+  if (h->gemm.impl < 1 || h->gemm.impl > 3) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..3"); }
+  int terms = cfg->split_terms;
+  if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
+  h->gemm.n_terms = (terms == 1) ? 1 : 3;
+  *out = h;
+  return ZETT_OK;
+}
+
+int zett_hn_set_weight(zett_hn* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
+  if (!h || !name || !data || ndim < 0 || ndim > 4) return fail(ZETT_ERR_INVALID, "bad argument");
+  if (h->finalized) return fail(ZETT_ERR_STATE, "set_weight after finalize");
+  ZETT_CUDA(cudaSetDevice(h->gemm.dev.device));
+  const std::string key(name);
+  auto ends_with = [&](const char* suf) { const size_t n = strlen(suf); return key.size() >= n && key.compare(key.size() - n, n, suf) == 0; };
+  if (key == "model.embeddings.word_embeddings.weight" || ends_with("position_ids") || ends_with("token_type_ids")) return ZETT_OK;
+  Staged st;
+  st.shape.assign(shape, shape + ndim);
+  const long long n = st.numel();
+  if (n <= 0) return fail(ZETT_ERR_INVALID, "empty weight " + key);
+  auto old = h->staged.find(key);
+  if (old != h->staged.end()) { cudaFree(old->second.dev); h->staged.erase(old); }
+  ZETT_CUDA(cudaMalloc(&st.dev, sizeof(float) * n));
+  if (dtype == ZETT_F32) {
+    ZETT_CUDA(cudaMemcpy(st.dev, data, sizeof(float) * n, cudaMemcpyDefault));
+  } else if (dtype == ZETT_F16 || dtype == ZETT_BF16) {
+    uint16_t* tmp;
+    ZETT_CUDA(cudaMalloc(&tmp, 2 * n));
+    ZETT_CUDA(cudaMemcpy(tmp, data, 2 * n, cudaMemcpyDefault));
+    convert_to_f32_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 4096)), 256>>>(tmp, n, st.dev, dtype);
+    ZETT_CUDA(cudaDeviceSynchronize());
+    cudaFree(tmp);
+  } else {
+    cudaFree(st.dev);
+    return fail(ZETT_ERR_INVALID, "unknown dtype code");
+  }
+  h->staged.emplace(key, std::move(st));
+  return ZETT_OK;
+}
+
+int zett_hn_finalize(zett_hn* h) {
+  if (!h) return fail(ZETT_ERR_INVALID, "null handle");
+  if (h->finalized) return ZETT_OK;
+  ZETT_CUDA(cudaSetDevice(h->gemm.dev.device));
+  const zett_hn_config& c = h->cfg;
+  const int H = h->H, I = h->I, D = h->D, E = h->E;
+  (void)I;
+  // squeeze [1, X] scalers to [X]
+  for (const char* nm : {"in_scaler.w", "in_scaler.b", "scaler.w", "scaler.b", "out_scaler.w", "out_scaler.b"}) {
+    auto it = h->staged.find(nm);
+    if (it != h->staged.end() && it->second.shape.size() == 2 && it->second.shape[0] == 1) it->second.shape.erase(it->second.shape.begin());
+  }
+  ZETT_TRY(take_vector(h, "fallback_embeddings.weight", {h->n_fallback, E}, &h->fallback));
+  ZETT_TRY(make_linear(h, {"input_projection.0"}, H, E, &h->in_proj0));
+  ZETT_TRY(make_projector(h, "input_projection.1.", &h->in_proj1));
+  float* type_tab;
+  ZETT_TRY(take_vector(h, "model.embeddings.token_type_embeddings.weight", {1, H}, &type_tab));
+  h->type0 = type_tab;
+  ZETT_TRY(take_vector(h, "model.embeddings.position_embeddings.weight", {c.max_position_embeddings, H}, &h->pos_table));
+  ZETT_TRY(take_vector(h, "model.embeddings.LayerNorm.weight", {H}, &h->emb_ln_w));
+  ZETT_TRY(take_vector(h, "model.embeddings.LayerNorm.bias", {H}, &h->emb_ln_b));
+  h->layers.resize(c.hn_n_layers);
+  for (int l = 0; l < c.hn_n_layers; ++l) {
+    const std::string p = "model.encoder.layer." + std::to_string(l) + ".";
+    EncoderLayer& ly = h->layers[l];
+    ZETT_TRY(make_linear(h, {p + "attention.self.query", p + "attention.self.key", p + "attention.self.value"}, H, H, &ly.qkv));
+    ZETT_TRY(make_linear(h, {p + "attention.output.dense"}, H, H, &ly.attn_out));
+    ZETT_TRY(take_vector(h, p + "attention.output.LayerNorm.weight", {H}, &ly.ln1_w));
+    ZETT_TRY(take_vector(h, p + "attention.output.LayerNorm.bias", {H}, &ly.ln1_b));
+    ZETT_TRY(make_linear(h, {p + "intermediate.dense"}, h->I, H, &ly.inter));
+    ZETT_TRY(make_linear(h, {p + "output.dense"}, H, h->I, &ly.out));
+    ZETT_TRY(take_vector(h, p + "output.LayerNorm.weight", {H}, &ly.ln2_w));
+    ZETT_TRY(take_vector(h, p + "output.LayerNorm.bias", {H}, &ly.ln2_b));
+  }
+  ZETT_TRY(make_projector(h, "output_projection.0.", &h->head_in));
+  if (c.hn_single_head) {
+    ZETT_TRY(make_linear(h, {"output_projection.1"}, E, H, &h->out_in));  // [E = D or 2D, H]; halves are row slices
+  } else {
+    ZETT_TRY(make_linear(h, {"output_projection.1"}, D, H, &h->out_in));
+    if (c.separate_out_embeddings) {
+      ZETT_TRY(make_projector(h, "output_projection_out.0.", &h->head_out));
+      ZETT_TRY(make_linear(h, {"output_projection_out.1"}, D, H, &h->out_out));
+    }
+  }
+  if (c.hn_rescale_embeddings) {
+    ZETT_TRY(take_vector(h, "in_scaler.w", {E}, &h->in_scale_w));
+    ZETT_TRY(take_vector(h, "in_scaler.b", {E}, &h->in_scale_b));
+    ZETT_TRY(take_vector(h, "scaler.w", {D}, &h->scale_w));
+    ZETT_TRY(take_vector(h, "scaler.b", {D}, &h->scale_b));
+    if (c.separate_out_embeddings) {
+      ZETT_TRY(take_vector(h, "out_scaler.w", {D}, &h->oscale_w));
+      ZETT_TRY(take_vector(h, "out_scaler.b", {D}, &h->oscale_b));
+    }
+  }
+  if (c.hn_predict_bias) {
+    ZETT_TRY(take_vector(h, "bias_projection.weight", {1, H}, &h->biasproj_w));
+    ZETT_TRY(take_vector(h, "bias_projection.bias", {1}, &h->biasproj_b));
+  }
+  if (c.hn_embed_lang_id) {
+    float* lang;
+    ZETT_TRY(staged_get(h, "lang_embeddings.weight", {c.n_langs, H}, &lang));
+    ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&h->lang_pre), sizeof(float) * static_cast<size_t>(c.n_langs) * H, false));
+    lang_pre_kernel<<<64, 256>>>(lang, h->type0, h->pos_table + static_cast<long long>(h->L) * H, c.n_langs, H, h->lang_pre);
+    ZETT_CUDA(cudaDeviceSynchronize());
+  }
+  for (auto& kv : h->staged) cudaFree(kv.second.dev);  // anything left is unused by this configuration
+  h->staged.clear();
+  ZETT_CUDA(cudaDeviceSynchronize());
+  h->finalized = true;
+  return ZETT_OK;
+}
+
+size_t zett_hn_workspace_bytes(const zett_hn* h, int64_t n_rows) {
+  if (!h) return 0;
+  const long long rows = std::min<long long>(std::max<int64_t>(n_rows, 1), h->cfg.max_rows_per_pass);
+  return workspace_bytes_for(h, rows);
+}
+
+int zett_hn_forward(zett_hn* h, const int32_t* surface_forms_dev, int64_t n_rows, const float* source_emb_dev,
+                    int64_t v0_rows, int32_t lang_index, float* pred_in_dev, float* pred_out_dev, float* pred_bias_dev,
+                    int64_t ld_pred, int64_t ld_bias, void* cuda_stream) {
+  if (!h) return fail(ZETT_ERR_INVALID, "null handle");
+  if (!h->finalized) return fail(ZETT_ERR_STATE, "zett_hn_forward before zett_hn_finalize");
+  if (n_rows < 0) return fail(ZETT_ERR_INVALID, "n_rows < 0");
+  if (!surface_forms_dev || !source_emb_dev || !pred_in_dev || !pred_bias_dev) return fail(ZETT_ERR_INVALID, "null device pointer");
+  const bool separate = h->cfg.separate_out_embeddings != 0;
+  if (separate && !pred_out_dev) return fail(ZETT_ERR_INVALID, "pred_out is required when separate_out_embeddings is set");
+  if (v0_rows < h->cfg.original_vocab_size)
+    return fail(ZETT_ERR_INVALID, "source_embeddings has fewer rows than original_vocab_size");
+  if (h->cfg.hn_embed_lang_id && (lang_index < 0 || lang_index >= h->cfg.n_langs))
+    return fail(ZETT_ERR_INVALID, "lang_index out of range for a hypernet with hn_embed_lang_id");
+  if (ld_pred == 0) ld_pred = h->D;
+  if (ld_bias == 0) ld_bias = 1;
+  if (ld_pred < h->D || ld_pred % 4 || ld_bias < 1) return fail(ZETT_ERR_INVALID, "ld_pred must be a multiple of 4 and >= D; ld_bias >= 1");
+  ZETT_CUDA(cudaSetDevice(h->gemm.dev.device));
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const long long per_pass = h->cfg.max_rows_per_pass;
+  ZETT_TRY(ensure_workspace(h, std::min<long long>(std::max<int64_t>(n_rows, 1), per_pass)));
+  h->gemm.launches = 0;
+  h->gemm.events_used = 0;
+  h->stats = zett_hn_stats{};
+  h->stats.rows = n_rows;
+  const long long first_pass = h->passes;
+  for (long long r0 = 0; r0 < n_rows; r0 += per_pass) {
+    const int rows = static_cast<int>(std::min<long long>(per_pass, n_rows - r0));
+    ZETT_TRY(forward_pass(h, surface_forms_dev + r0 * h->L, rows, source_emb_dev, v0_rows, lang_index,
+                          pred_in_dev + r0 * ld_pred, separate ? pred_out_dev + r0 * ld_pred : nullptr,
+                          pred_bias_dev + r0 * ld_bias, ld_pred, ld_bias, stream));
+  }
+  h->stats.kernel_launches = h->gemm.launches;
+  h->stats.packed_positions = -(h->passes - first_pass);  // negative = number of passes whose counts are still on the device
+  return ZETT_OK;
+}
+
+int zett_hn_check(zett_hn* h, void* cuda_stream) {
+  if (!h) return fail(ZETT_ERR_INVALID, "null handle");
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) {
+    return fail(ZETT_ERR_CUDA, std::string("kernel fault: ") + cudaGetErrorString(e) + watchdog_text());
+  }
+  if (h->gemm.timing && h->gemm.events_used) {
+    long long n = 0;
+    h->stats.gemm_ms = h->gemm.collect_ms(&n);
+    h->stats.gemm_launches = n;
+  }
+  if (h->stats.packed_positions < 0 && h->ws.counts_all) {
+    const long long n_pass = std::min<long long>(-h->stats.packed_positions, kMaxPassSlots);
+    std::vector<int> host(static_cast<size_t>(kMaxPassSlots) * kCntSlots);
+    ZETT_CUDA(cudaMemcpy(host.data(), h->ws.counts_all, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
+    long long t1 = 0, t2 = 0, rows = 0;
+    int bad = 0;
+    for (long long i = 0; i < n_pass; ++i) {
+      const long long slot = ((h->passes - 1 - i) % kMaxPassSlots + kMaxPassSlots) % kMaxPassSlots;
+      t1 += host[slot * kCntSlots + kCntSurface];
+      t2 += host[slot * kCntSlots + kCntEncoder];
+      rows += host[slot * kCntSlots + kCntRows];
+      bad |= host[slot * kCntSlots + kCntBadId];
+    }
+    h->stats.packed_positions = t1;
+    h->stats.encoder_positions = t2;
+    h->stats.flops_executed = h->coef_t1 * t1 + h->coef_t2 * t2 + h->coef_rows * rows;
+    if (bad)
+      return fail(ZETT_ERR_INDEX, "surface-form id outside [0, original_vocab_size + max(hn_n_extra_tokens, 1))");
+  }
+  return ZETT_OK;
+}
+
+int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out) {
+  if (!h || !out) return fail(ZETT_ERR_INVALID, "null argument");
+  *out = h->stats;
+  return ZETT_OK;
+}
+
+int zett_hn_set_timing(zett_hn* h, int enable) {
+  if (!h) return fail(ZETT_ERR_INVALID, "null handle");
+  h->gemm.timing = enable != 0;
+  h->gemm.events_used = 0;
+  return ZETT_OK;
+}
+
+void zett_hn_destroy(zett_hn* h) {
+  if (!h) return;
+  cudaSetDevice(h->gemm.dev.device);
+  cudaDeviceSynchronize();
+  for (cudaEvent_t e : h->gemm.events) cudaEventDestroy(e);
+  free_workspace(h);
+  for (auto& kv : h->staged) cudaFree(kv.second.dev);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev, float* out_dev, int64_t m, int64_t n,
+                  int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms, void* cuda_stream) {
+  if (!a_dev || !w_dev || !out_dev || m <= 0 || n <= 0 || k <= 0) return fail(ZETT_ERR_INVALID, "bad argument");
+  if ((m * k) % 4 || (n * k) % 4 || k % 8 || n % 8) return fail(ZETT_ERR_INVALID, "sizes must be multiples of 8");
+  GemmEngine eng;
+  ZETT_TRY(query_device(&eng.dev));
+  ZETT_TRY(set_kernel_attrs(&eng.dev));
+  eng.impl = impl == 0 ? 2 : impl;
+  eng.n_terms = split_terms == 1 ? 1 : 3;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  uint16_t *pa = nullptr, *pw = nullptr;
+  ZETT_CUDA(cudaMalloc(&pa, sizeof(uint16_t) * 2 * m * k));
+  ZETT_CUDA(cudaMalloc(&pw, sizeof(uint16_t) * 2 * n * k));
+  auto cleanup = [&]() { cudaFree(pa); cudaFree(pw); };
+  const int two = eng.n_terms == 3;
+  split_planes_kernel<<<1184, 256, 0, stream>>>(a_dev, m * k / 4, pa, two ? pa + m * k : nullptr, eng.split_fmt);
+  split_planes_kernel<<<1184, 256, 0, stream>>>(w_dev, n * k / 4, pw, two ? pw + n * k : nullptr, eng.split_fmt);
+  GemmArgs g;
+  g.a = pa; g.a_rows = m; g.a_plane_stride = m * k;
+  g.w = pw; g.w_plane_stride = n * k;
+  g.n = static_cast<int>(n); g.k = static_cast<int>(k); g.m_host = static_cast<int>(m);
+  g.ep.bias = bias_dev; g.ep.act = act; g.ep.out_f32 = out_dev; g.ep.ld_out = n; g.ep.split_fmt = eng.split_fmt;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = eng.launch(g, stream);  // warm-up / the result
+  if (rc == ZETT_OK && elapsed_ms) {
+    cudaEventRecord(e0, stream);
+    for (int i = 0; i < std::max(iters, 1) && rc == ZETT_OK; ++i) rc = eng.launch(g, stream);
+    cudaEventRecord(e1, stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (rc == ZETT_OK && e != cudaSuccess) {
+    rc = fail(ZETT_ERR_CUDA, std::string("GEMM kernel fault: ") + cudaGetErrorString(e) + watchdog_text());
+  }
+  if (rc == ZETT_OK && elapsed_ms) cudaEventElapsedTime(elapsed_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,515 @@
+// The non-GEMM kernels of the hypernetwork forward, plus the SIMT fp32 GEMM used as the on-device checker.
+//
+//   pack_rows_kernel        surface-form rows -> packed (pad-free) position lists          (modeling_hypernet.py:170-177,190)
+//   gather_rescale_kernel   ids -> source / fallback embedding rows, in_scaler, 16-bit split (modeling_hypernet.py:179-188)
+//   layernorm_kernel        (x [+ residual] [+ type/position embeddings]) -> LayerNorm -> fp32 + split planes
+//   attention_kernel        per (row, head) softmax(q k^T / sqrt(dh) + mask) v over <= S packed positions
+//   split_planes_kernel     fp32 -> two 16-bit planes (weights at load time)
+//   gemm_simt_kernel        same contract as gemm_tcgen05_kernel, CUDA cores, for checking
+//
+// Packing.  A surface-form row holds L ids, most of them pad (mean non-pad length ~2.9 of 7 on the benchmark
+// vocabularies).  Pad positions act only as masked keys and their own outputs never reach position 0, so they are
+// dropped: every per-position tensor is stored for the kept positions only, rows back to back.  Kept = non-pad
+// positions plus position 0 (always the query that is read out).  A row with no valid key at all attends uniformly
+// over all S positions in the reference (additive finfo.min mask, eager attention); such rows keep all L positions
+// and are flagged so that the attention kernel reproduces the uniform weights.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace zett {
+
+constexpr int kPackThreads = 1024;
+constexpr int kMaxSurfaceLen = 32;
+
+// counts[] slots
+enum : int { kCntSurface = 0, kCntEncoder = 1, kCntBadId = 2, kCntRows = 3, kCntSlots = 8 };
+
+struct PackParams {
+  const int32_t* ids;    // [n_rows, L]
+  int n_rows, L;
+  int pad_id, v0, n_fallback;  // n_fallback = max(hn_n_extra_tokens, 1)
+  int lang_slot;               // 1 when a lang-id position is appended to every row
+  int* counts;                 // [kCntSlots]
+  int* row_start1;             // [n_rows + 1]  surface packing (input projection)
+  int* row_start2;             // [n_rows + 1]  encoder packing (surface positions + lang slot)
+  int* tok_src;                // [T1]  >= 0: source row, < 0: -1 - fallback row
+  int* tok_pos;                // [T1]  position id
+  int* tok_enc;                // [T1]  index of this position in the encoder packing
+  int* tok1_row;               // [T1]  row of this position
+  int* lang_enc;               // [n_rows] index of the lang slot in the encoder packing (lang_slot only)
+  int* tok2_row;               // [T2]
+  unsigned char* tok2_valid;   // [T2]  1 = usable as attention key
+};
+
+__device__ __forceinline__ uint32_t kept_mask(const int32_t* row, int L, int pad_id, int lang_slot, uint32_t& nonpad) {
+  nonpad = 0;
+  for (int p = 0; p < L; ++p) nonpad |= (row[p] != pad_id ? 1u : 0u) << p;
+  uint32_t kept = nonpad | 1u;
+  if (!lang_slot && nonpad == 0) kept = (L >= 32) ? 0xFFFFFFFFu : ((1u << L) - 1u);
+  return kept;
+}
+
+// One block; thread i owns a contiguous slice of rows.  Two walks over the slice: count, block scan, emit.
+__global__ void __launch_bounds__(kPackThreads, 1) pack_rows_kernel(const PackParams p) {
+  __shared__ int warp_sums[32];
+  __shared__ int warp_sums2[32];
+  const int tid = threadIdx.x;
+  const int rows_per_thread = (p.n_rows + kPackThreads - 1) / kPackThreads;
+  const int r0 = min(p.n_rows, tid * rows_per_thread);
+  const int r1 = min(p.n_rows, r0 + rows_per_thread);
+  const int id_limit = p.v0 + p.n_fallback;
+
+  int local = 0;
+  int bad = 0;
+  for (int r = r0; r < r1; ++r) {
+    const int32_t* row = p.ids + static_cast<long long>(r) * p.L;
+    uint32_t nonpad;
+    local += __popc(kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad));
+    for (int q = 0; q < p.L; ++q) bad |= (row[q] < 0 || row[q] >= id_limit) ? 1 : 0;
+  }
+  // block-wide exclusive scan of `local`
+  const int lane = tid & 31, warp = tid >> 5;
+  int incl = local;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_sums2[lane] = wi - w;  // exclusive prefix of the warp totals
+    if (lane == 31) {
+      p.counts[kCntSurface] = wi;
+      p.counts[kCntEncoder] = wi + (p.lang_slot ? p.n_rows : 0);
+      p.counts[kCntRows] = p.n_rows;
+      p.row_start1[p.n_rows] = wi;
+      p.row_start2[p.n_rows] = wi + (p.lang_slot ? p.n_rows : 0);
+    }
+  }
+  __syncthreads();
+  if (bad) atomicOr(&p.counts[kCntBadId], 1);
+  int t1 = warp_sums2[warp] + incl - local;  // first surface position of row r0
+
+  for (int r = r0; r < r1; ++r) {
+    const int32_t* row = p.ids + static_cast<long long>(r) * p.L;
+    uint32_t nonpad;
+    const uint32_t kept = kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad);
+    const int t2_base = t1 + (p.lang_slot ? r : 0);
+    p.row_start1[r] = t1;
+    p.row_start2[r] = t2_base;
+    int j = 0;
+    for (int q = 0; q < p.L; ++q) {
+      if (!((kept >> q) & 1u)) continue;
+      int id = row[q];
+      id = max(0, min(id, id_limit - 1));  // never read out of bounds; kCntBadId reports the violation
+      p.tok_src[t1 + j] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
+      p.tok_pos[t1 + j] = q;
+      p.tok_enc[t1 + j] = t2_base + j;
+      p.tok1_row[t1 + j] = r;
+      p.tok2_row[t2_base + j] = r;
+      p.tok2_valid[t2_base + j] = static_cast<unsigned char>((nonpad >> q) & 1u);
+      ++j;
+    }
+    if (p.lang_slot) {
+      p.lang_enc[r] = t2_base + j;
+      p.tok2_row[t2_base + j] = r;
+      p.tok2_valid[t2_base + j] = 1;
+    }
+    t1 += j;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Gather + rescale + split.  One CTA streams whole embedding rows: each row is fetched with ONE bulk async copy
+// (cp.async.bulk, the TMA engine's linear mode) into a double-buffered shared-memory stage, so the HBM reads are
+// full-line and independent of the thread mapping; the threads then apply  w * x + b  (in_scaler, not for fallback
+// rows), split into the two 16-bit planes the input-projection GEMM consumes and store 16 bytes per plane per thread.
+// Algorithmic bytes per position: 4 E read + 4 E written.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+
+struct GatherParams {
+  const float* source;     // [v0_rows, E]
+  long long v0_rows;
+  const float* fallback;   // [n_fallback, E]
+  const float* scale_w;    // [E] or nullptr
+  const float* scale_b;
+  const int* tok_src;
+  const int* n_tok;        // device count
+  int E;
+  int split_fmt;
+  uint16_t* out_p0;        // [cap, E]
+  uint16_t* out_p1;        // nullable (single-plane mode)
+};
+
+__global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const GatherParams p) {
+  extern __shared__ __align__(128) uint8_t gsmem[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  float* stage[2] = {reinterpret_cast<float*>(gsmem), reinterpret_cast<float*>(gsmem) + p.E};
+  const uint32_t bar[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+  const int n_tok = *p.n_tok;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.E) * 4u;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(bar[0], 1);
+    mbar_init(bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto row_ptr = [&](int t) -> const float* {
+    const int s = __ldg(p.tok_src + t);
+    if (s >= 0) return p.source + static_cast<long long>(min(static_cast<long long>(s), p.v0_rows - 1)) * p.E;
+    return p.fallback + static_cast<long long>(-1 - s) * p.E;
+  };
+  int t = blockIdx.x;
+  if (tid == 0 && t < n_tok) {
+    mbar_expect_tx(bar[0], row_bytes);
+    bulk_load_1d(smem_u32(stage[0]), row_ptr(t), row_bytes, bar[0]);
+  }
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  for (; t < n_tok; t += gridDim.x, buf ^= 1) {
+    const int t_next = t + gridDim.x;
+    if (tid == 0 && t_next < n_tok) {  // the other stage was released by the __syncthreads of the last iteration
+      mbar_expect_tx(bar[buf ^ 1], row_bytes);
+      bulk_load_1d(smem_u32(stage[buf ^ 1]), row_ptr(t_next), row_bytes, bar[buf ^ 1]);
+    }
+    mbar_wait(bar[buf], phase[buf], 16);
+    phase[buf] ^= 1u;
+    const bool rescale = p.scale_w != nullptr && __ldg(p.tok_src + t) >= 0;
+    const float* x = stage[buf];
+    uint16_t* o0 = p.out_p0 + static_cast<long long>(t) * p.E;
+    uint16_t* o1 = p.out_p1 ? p.out_p1 + static_cast<long long>(t) * p.E : nullptr;
+    for (int e = tid * 8; e < p.E; e += kGatherThreads * 8) {
+      float v[8];
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(x + e);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(x + e + 4);
+      if (rescale) {
+        float w[8], b[8];
+        *reinterpret_cast<float4*>(w) = __ldg(reinterpret_cast<const float4*>(p.scale_w + e));
+        *reinterpret_cast<float4*>(w + 4) = __ldg(reinterpret_cast<const float4*>(p.scale_w + e + 4));
+        *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(p.scale_b + e));
+        *reinterpret_cast<float4*>(b + 4) = __ldg(reinterpret_cast<const float4*>(p.scale_b + e + 4));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(__fmul_rn(w[i], v[i]), b[i]);  // Rescaler: w * x + b, two roundings
+      }
+      uint16_t a[8], c[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) split16(v[i], p.split_fmt, a[i], c[i]);
+      uint4 pa, pc;
+      pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
+      pa.z = a[4] | (uint32_t(a[5]) << 16); pa.w = a[6] | (uint32_t(a[7]) << 16);
+      pc.x = c[0] | (uint32_t(c[1]) << 16); pc.y = c[2] | (uint32_t(c[3]) << 16);
+      pc.z = c[4] | (uint32_t(c[5]) << 16); pc.w = c[6] | (uint32_t(c[7]) << 16);
+      *reinterpret_cast<uint4*>(o0 + e) = pa;
+      if (o1) *reinterpret_cast<uint4*>(o1 + e) = pc;
+    }
+    __syncthreads();  // everyone is done reading stage[buf] before it is refilled two iterations from now
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// LayerNorm over H with the additions that precede it in the reference:
+//     v = a[t] (+ res[t]) (+ vec0) (+ table[idx])        y = (v - mean) / sqrt(var + eps) * gamma + beta
+// ProjectorBlock.ln (eps 1e-6, modeling_hypernet.py:33,40), RobertaEmbeddings (type + position embeddings, eps 1e-5),
+// RobertaSelfOutput / RobertaOutput (residual, eps 1e-5).  Two-pass statistics in fp32 like torch.  One CTA per row.
+// Outputs: fp32 (the residual stream) and the split planes the next GEMM reads; optionally scattered through
+// out_index (surface packing -> encoder packing), optionally duplicated for the first position of every row into
+// compact [n_rows, H] buffers (the pruned last layer reads only those), optionally a dot product with a vector
+// (bias_projection, modeling_hypernet.py:260-265).
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 8;  // float4 per thread: H <= 4 * 8 * blockDim
+
+struct LnParams {
+  const float* a;
+  long long lda;             // 0 broadcasts one vector to every row
+  const float* res;          // nullable, row stride H
+  const float* vec0;         // nullable [H]
+  const float* table;        // nullable [*, H]
+  const int* table_idx;      // nullable -> table_const
+  int table_const;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int H;
+  const int* n_dev;          // nullable -> n_host
+  int n_host;
+  const int* out_index;      // nullable
+  float* out_f32;            // nullable [*, H]
+  uint16_t* out_p0;          // nullable [*, H]
+  uint16_t* out_p1;
+  int split_fmt;
+  const int* tok_row;        // nullable: enables the compact copy for positions with row_start[tok_row[t]] == t
+  const int* row_start;
+  float* c_f32;
+  uint16_t* c_p0;
+  uint16_t* c_p1;
+  const float* dot_w;        // nullable [H]
+  const float* dot_b;        // [1]
+  float* dot_out;            // [n * dot_ld]
+  long long dot_ld;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nwarp) ? red[lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+  return t;
+}
+
+__device__ __forceinline__ void store_split4(uint16_t* p0, uint16_t* p1, long long off, const float4 y, int fmt) {
+  uint16_t a[4], b[4];
+  split16(y.x, fmt, a[0], b[0]);
+  split16(y.y, fmt, a[1], b[1]);
+  split16(y.z, fmt, a[2], b[2]);
+  split16(y.w, fmt, a[3], b[3]);
+  uint2 pa, pb;
+  pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
+  pb.x = b[0] | (uint32_t(b[1]) << 16); pb.y = b[2] | (uint32_t(b[3]) << 16);
+  *reinterpret_cast<uint2*>(p0 + off) = pa;
+  if (p1) *reinterpret_cast<uint2*>(p1 + off) = pb;
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  __shared__ float red[32];
+  const int n = p.n_dev ? *p.n_dev : p.n_host;
+  const int H4 = p.H >> 2;
+  for (int t = blockIdx.x; t < n; t += gridDim.x) {
+    float4 v[kLnMaxVec];
+    const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(t) * p.lda);
+    const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res + static_cast<long long>(t) * p.H) : nullptr;
+    const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) : nullptr;
+    const float4* e4 = nullptr;
+    if (p.table) {
+      const int idx = p.table_idx ? __ldg(p.table_idx + t) : p.table_const;
+      e4 = reinterpret_cast<const float4*>(p.table + static_cast<long long>(idx) * p.H);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnMaxVec; ++c) {
+      const int i = threadIdx.x + c * blockDim.x;
+      if (i < H4) {
+        float4 x = a4[i];
+        if (r4) { const float4 y = r4[i]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        if (z4) { const float4 y = __ldg(z4 + i); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        if (e4) { const float4 y = __ldg(e4 + i); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        v[c] = x;
+        s += (x.x + x.y) + (x.z + x.w);
+      }
+    }
+    const float mean = block_sum(s, red) / static_cast<float>(p.H);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kLnMaxVec; ++c) {
+      const int i = threadIdx.x + c * blockDim.x;
+      if (i < H4) {
+        const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float var = block_sum(q, red) / static_cast<float>(p.H);
+    const float rstd = 1.0f / sqrtf(var + p.eps);
+
+    const long long o = static_cast<long long>(p.out_index ? __ldg(p.out_index + t) : t) * p.H;
+    long long co = -1;
+    if (p.tok_row) {
+      const int r = __ldg(p.tok_row + t);
+      if (__ldg(p.row_start + r) == t) co = static_cast<long long>(r) * p.H;
+    }
+    float dot = 0.f;
+    const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(p.beta);
+    const float4* w4 = p.dot_w ? reinterpret_cast<const float4*>(p.dot_w) : nullptr;
+#pragma unroll
+    for (int c = 0; c < kLnMaxVec; ++c) {
+      const int i = threadIdx.x + c * blockDim.x;
+      if (i < H4) {
+        const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+        float4 y;
+        y.x = (v[c].x - mean) * rstd * g.x + b.x;
+        y.y = (v[c].y - mean) * rstd * g.y + b.y;
+        y.z = (v[c].z - mean) * rstd * g.z + b.z;
+        y.w = (v[c].w - mean) * rstd * g.w + b.w;
+        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o + 4 * i) = y;
+        if (p.out_p0) store_split4(p.out_p0, p.out_p1, o + 4 * i, y, p.split_fmt);
+        if (co >= 0) {
+          if (p.c_f32) *reinterpret_cast<float4*>(p.c_f32 + co + 4 * i) = y;
+          if (p.c_p0) store_split4(p.c_p0, p.c_p1, co + 4 * i, y, p.split_fmt);
+        }
+        if (w4) {
+          const float4 w = __ldg(w4 + i);
+          dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
+        }
+      }
+    }
+    if (w4) {
+      const float d = block_sum(dot, red);
+      if (threadIdx.x == 0) p.dot_out[static_cast<long long>(t) * p.dot_ld] = d + __ldg(p.dot_b);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Attention over the <= S packed positions of one row: one warp per (row, head); lane l holds elements l, l + 32, ...
+// of the head vectors (coalesced 128-byte reads), dot products reduce with warp shuffles, softmax is an online
+// running max / sum in fp32 (HF eager attention: scores * dh^-0.5 + additive mask, softmax, @ V).
+// A row without any valid key gets uniform weights over all of its positions (what finfo.min + softmax yields).
+// row0_only: only the first position of each row is a query (pruned last layer); q and out are then indexed by row.
+// -------------------------------------------------------------------------------------------------------------------
+struct AttnParams {
+  const float* q; long long ldq;
+  const float* k; long long ldk;
+  const float* v; long long ldv;
+  const int* row_start;          // encoder packing [n_rows + 1]
+  const unsigned char* valid;    // [T2]
+  int n_rows, n_heads, dh;
+  float scale;
+  int row0_only;
+  uint16_t* out_p0;              // [*, H]
+  uint16_t* out_p1;
+  long long ld_out;
+  int split_fmt;
+};
+
+template <int DPL>
+__global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= static_cast<long long>(p.n_rows) * p.n_heads) return;
+  const int r = static_cast<int>(wid / p.n_heads);
+  const int h = static_cast<int>(wid % p.n_heads);
+  const int t0 = __ldg(p.row_start + r), t1 = __ldg(p.row_start + r + 1);
+  const int n = t1 - t0;
+  const int hoff = h * p.dh + lane;
+  bool any_valid = false;
+  for (int j = 0; j < n; ++j) any_valid |= __ldg(p.valid + t0 + j) != 0;
+  const int n_q = p.row0_only ? 1 : n;
+  for (int i = 0; i < n_q; ++i) {
+    const long long qi = p.row0_only ? r : (t0 + i);
+    float qv[DPL];
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) qv[d] = __ldg(p.q + qi * p.ldq + hoff + 32 * d);
+    float m = -INFINITY, l = 0.f, acc[DPL];
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
+    for (int j = 0; j < n; ++j) {
+      if (any_valid && !__ldg(p.valid + t0 + j)) continue;  // masked key: weight exactly 0
+      float s = 0.f;
+      if (any_valid) {
+        const float* kj = p.k + static_cast<long long>(t0 + j) * p.ldk + hoff;
+#pragma unroll
+        for (int d = 0; d < DPL; ++d) s += qv[d] * __ldg(kj + 32 * d);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        s *= p.scale;
+      }
+      const float m_new = fmaxf(m, s);
+      const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
+      const float w = expf(s - m_new);
+      l = l * corr + w;
+      const float* vj = p.v + static_cast<long long>(t0 + j) * p.ldv + hoff;
+#pragma unroll
+      for (int d = 0; d < DPL; ++d) acc[d] = acc[d] * corr + w * __ldg(vj + 32 * d);
+      m = m_new;
+    }
+    const float inv = 1.0f / l;
+    const long long oi = (p.row0_only ? r : (t0 + i)) * p.ld_out + hoff;
+#pragma unroll
+    for (int d = 0; d < DPL; ++d) {
+      uint16_t a, b;
+      split16(acc[d] * inv, p.split_fmt, a, b);
+      p.out_p0[oi + 32 * d] = a;
+      if (p.out_p1) p.out_p1[oi + 32 * d] = b;
+    }
+  }
+}
+
+// fp32 [rows, cols] -> 16-bit planes (same layout); rows * cols must be a multiple of 4
+__global__ void split_planes_kernel(const float* __restrict__ x, long long n4, uint16_t* p0, uint16_t* p1, int fmt) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 y = __ldg(reinterpret_cast<const float4*>(x) + i);
+    store_split4(p0, p1, 4 * i, y, fmt);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// SIMT checker GEMM: identical contract and identical product terms (A0 B0 + A1 B0 + A0 B1, fp32 accumulation) as the
+// tcgen05 kernel, on CUDA cores.  128 x 32 output tile per CTA, one thread per row.  Used by the tests to validate
+// the tensor-core path on the device and selectable (gemm_impl = 3) to bisect a failure; never the default.
+// -------------------------------------------------------------------------------------------------------------------
+struct SimtGemmParams {
+  const uint16_t* a0; const uint16_t* a1;  // [M, K] planes (a1 nullable)
+  const uint16_t* w0; const uint16_t* w1;  // [N, K] planes (w1 nullable)
+  int m_host; const int* m_dev;
+  int n, k;
+  int split_fmt;
+};
+
+__device__ __forceinline__ float plane_to_float(uint16_t u, int fmt) {
+  return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
+}
+
+__global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, const EpilogueParams ep) {
+  __shared__ float As0[128][33], As1[128][33], Ws0[32][33], Wsum[32][33];
+  const int M = s.m_dev ? *s.m_dev : s.m_host;
+  const int row0 = blockIdx.y * 128, col0 = blockIdx.x * 32;
+  if (row0 >= M) return;
+  const int tid = threadIdx.x;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int k0 = 0; k0 < s.k; k0 += 32) {
+    for (int i = tid; i < 128 * 32; i += 128) {
+      const int r = i >> 5, c = i & 31;
+      const long long gr = row0 + r;
+      float x0 = 0.f, x1 = 0.f;
+      if (gr < M && k0 + c < s.k) {
+        x0 = plane_to_float(s.a0[gr * s.k + k0 + c], s.split_fmt);
+        if (s.a1) x1 = plane_to_float(s.a1[gr * s.k + k0 + c], s.split_fmt);
+      }
+      As0[r][c] = x0;
+      As1[r][c] = x1;
+    }
+    for (int i = tid; i < 32 * 32; i += 128) {
+      const int r = i >> 5, c = i & 31;
+      const long long gn = col0 + r;
+      float y0 = 0.f, y1 = 0.f;
+      if (gn < s.n && k0 + c < s.k) {
+        y0 = plane_to_float(s.w0[gn * s.k + k0 + c], s.split_fmt);
+        if (s.w1) y1 = plane_to_float(s.w1[gn * s.k + k0 + c], s.split_fmt);
+      }
+      Ws0[r][c] = y0;
+      Wsum[r][c] = y0 + y1;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < 32; ++kk) {
+      const float x0 = As0[tid][kk], x1 = As1[tid][kk];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] += x0 * Wsum[c][kk] + x1 * Ws0[c][kk];
+    }
+    __syncthreads();
+  }
+  const int row = row0 + tid;
+  if (row < M) epilogue_store32(ep, row, col0, min(32, s.n - col0), acc);
+}
+
+}  // namespace zett

@@ -1,14 +1,15 @@
 // Thin inline-PTX wrappers for the Blackwell (sm_100a) features the hot path uses:
 // mbarrier, TMA (cp.async.bulk[.tensor]), tcgen05 (alloc / mma / commit / ld), clusters.
 // Every wait is bounded: a barrier that does not complete within kWatchdogNs records a code in
-// g_zett_watchdog and traps, so a protocol bug can never hang a GPU box.
+// the host-mapped record g_zett_watchdog points at (readable after the context died) and traps, so a protocol bug
+// can never hang a GPU box.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace zett {
 
-__device__ unsigned long long g_zett_watchdog[4];  // {code, blockIdx, aux0, aux1}
+__device__ unsigned long long* g_zett_watchdog = nullptr;  // -> pinned host {code, blockIdx, aux0, aux1}, set by the host
 constexpr unsigned long long kWatchdogNs = 8ull * 1000ull * 1000ull * 1000ull;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -67,10 +68,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __noinline__ void watchdog_fire(uint32_t code, uint32_t aux0, uint32_t aux1) {
-  g_zett_watchdog[0] = code;
-  g_zett_watchdog[1] = blockIdx.x;
-  g_zett_watchdog[2] = aux0;
-  g_zett_watchdog[3] = aux1;
+  volatile unsigned long long* w = g_zett_watchdog;
+  if (w) {
+    w[1] = blockIdx.x;
+    w[2] = aux0;
+    w[3] = aux1;
+    w[0] = code;
+  }
   __threadfence_system();
   __trap();
 }

@@ -10,7 +10,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .config import ZettHypernetConfig
+from .config import ZettHypernetConfig, weight_shapes
 
 # --------------------------------------------------------------------------------------------------
 # configs (hyper-parameters from the reference's shipped configs)
@@ -55,67 +55,6 @@ def config_names() -> List[str]:
 # --------------------------------------------------------------------------------------------------
 # weights
 # --------------------------------------------------------------------------------------------------
-def weight_shapes(cfg: ZettHypernetConfig) -> Dict[str, Tuple[int, ...]]:
-    """The reference's ``state_dict`` names and shapes (hf_hypernet/modeling_hypernet.py:46-154)."""
-    H, I, D = cfg.hn_hidden_size, cfg.hn_intermediate_size, cfg.n_embd
-    E = cfg.n_in_embd
-    s: Dict[str, Tuple[int, ...]] = {}
-    s["model.embeddings.word_embeddings.weight"] = (cfg.pad_token_id + 1, H)
-    s["model.embeddings.token_type_embeddings.weight"] = (1, H)
-    s["model.embeddings.position_embeddings.weight"] = (514, H)
-    s["model.embeddings.LayerNorm.weight"] = (H,)
-    s["model.embeddings.LayerNorm.bias"] = (H,)
-    for l in range(cfg.hn_n_layers):
-        p = f"model.encoder.layer.{l}."
-        for n in ("query", "key", "value"):
-            s[p + f"attention.self.{n}.weight"] = (H, H)
-            s[p + f"attention.self.{n}.bias"] = (H,)
-        s[p + "attention.output.dense.weight"] = (H, H)
-        s[p + "attention.output.dense.bias"] = (H,)
-        s[p + "attention.output.LayerNorm.weight"] = (H,)
-        s[p + "attention.output.LayerNorm.bias"] = (H,)
-        s[p + "intermediate.dense.weight"] = (I, H)
-        s[p + "intermediate.dense.bias"] = (I,)
-        s[p + "output.dense.weight"] = (H, I)
-        s[p + "output.dense.bias"] = (H,)
-        s[p + "output.LayerNorm.weight"] = (H,)
-        s[p + "output.LayerNorm.bias"] = (H,)
-    s["fallback_embeddings.weight"] = (max(cfg.hn_n_extra_tokens, 1), E)
-    s["input_projection.0.weight"] = (H, E)
-    s["input_projection.0.bias"] = (H,)
-
-    def projector(prefix):
-        s[prefix + "dense1.weight"] = (I, H)
-        s[prefix + "dense1.bias"] = (I,)
-        s[prefix + "dense2.weight"] = (H, I)
-        s[prefix + "dense2.bias"] = (H,)
-        s[prefix + "ln.weight"] = (H,)
-        s[prefix + "ln.bias"] = (H,)
-
-    projector("input_projection.1.")
-    projector("output_projection.0.")
-    s["output_projection.1.weight"] = (E if cfg.hn_single_head else D, H)
-    s["output_projection.1.bias"] = (E if cfg.hn_single_head else D,)
-    if cfg.separate_out_embeddings and not cfg.hn_single_head:
-        projector("output_projection_out.0.")
-        s["output_projection_out.1.weight"] = (D, H)
-        s["output_projection_out.1.bias"] = (D,)
-    if cfg.hn_rescale_embeddings:
-        s["in_scaler.w"] = (1, E)
-        s["in_scaler.b"] = (1, E)
-        s["scaler.w"] = (1, D)
-        s["scaler.b"] = (1, D)
-        if cfg.separate_out_embeddings:
-            s["out_scaler.w"] = (1, D)
-            s["out_scaler.b"] = (1, D)
-    if cfg.hn_predict_bias:
-        s["bias_projection.weight"] = (1, H)
-        s["bias_projection.bias"] = (1,)
-    if cfg.hn_embed_lang_id:
-        s["lang_embeddings.weight"] = (cfg.n_langs, H)
-    return s
-
-
 def make_weights(cfg: ZettHypernetConfig, seed: int = 0) -> Dict[str, np.ndarray]:
     """Random fp32 weights: Linear W ~ N(0, 1/fan_in), biases ~ N(0, 0.02^2),
     LayerNorm gamma = 1 + 0.1 N(0,1), beta = 0.1 N(0,1), embeddings ~ N(0, 0.02^2),
@@ -245,8 +184,12 @@ def make_bpe_merges(vocab: List[str]) -> Tuple[List[str], List[Tuple[str, str]]]
     return vocab, merges
 
 
-def make_hn_tokenizer(kind: str = "unigram", n_vocab: int = 32000, seed: int = 1, pad_token: str = "</s>"):
-    """A ``PreTrainedTokenizerFast`` wrapping a synthetic Unigram or BPE model, as ``tokenizer_to_use``."""
+def make_hn_tokenizer(kind: str = "unigram", n_vocab: int = 32000, seed: int = 1, pad_token: str = "</s>",
+                      fit_total: bool = False):
+    """A ``PreTrainedTokenizerFast`` wrapping a synthetic Unigram or BPE model, as ``tokenizer_to_use``.
+
+    BPE vocabularies grow by the intermediate merge symbols (about 3.5x); ``fit_total=True`` shrinks the piece list
+    until the FINAL vocabulary has at most ``n_vocab`` entries, so that every id is a valid source-embedding row."""
     from tokenizers import Tokenizer, models
     from transformers import PreTrainedTokenizerFast
 
@@ -254,7 +197,11 @@ def make_hn_tokenizer(kind: str = "unigram", n_vocab: int = 32000, seed: int = 1
     if kind == "unigram":
         model = models.Unigram([(t, float(s)) for t, s in zip(vocab, scores)], unk_id=3, byte_fallback=False)
     elif kind == "bpe":
+        base = n_vocab
         vocab, merges = make_bpe_merges(vocab)
+        while fit_total and len(vocab) > n_vocab:
+            base = max(300, int(base * min(0.97, n_vocab / len(vocab))))
+            vocab, merges = make_bpe_merges(make_hn_vocab(base, seed)[0])
         model = models.BPE(vocab={t: i for i, t in enumerate(vocab)}, merges=merges, unk_token="<unk>")
     else:
         raise ValueError(kind)
