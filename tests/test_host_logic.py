@@ -1,0 +1,94 @@
+"""Host-side logic that needs no GPU: the transfer driver's batching semantics (scripts/transfer.py:54-124) and the
+row-sharded multi-process path (world_size 2, gloo) with the oracle standing in for the kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import hypernet_oracle as ho
+from zett_b200 import parallel, synthetic
+from zett_b200.transfer import batched_inference, default_args
+
+
+def _fake_predict(sf, priors=None):
+    sf = np.asarray(sf, dtype=np.float32)
+    return sf[:, :4] * 2.0 + 1.0, sf[:, 1:5] - 3.0, sf.sum(axis=1)
+
+
+def test_batched_inference_equals_one_shot():
+    rng = np.random.default_rng(0)
+    sf = rng.integers(0, 1000, size=(1000, 7)).astype(np.int32)
+    cfg = synthetic.make_config("tiny")
+    cfg.hidden_size = 4
+    for bs in (64, 256, 1000, 4096):
+        got = batched_inference(sf, None, cfg, default_args(batch_size=bs), _fake_predict, rng=np.random.default_rng(1))
+        for g, w in zip(got, _fake_predict(sf)):
+            np.testing.assert_array_equal(g, w)
+    got = batched_inference(sf, None, cfg, default_args(batch_size=128), _fake_predict, embedding_path_out=None, bias_path=None)
+    assert got[1] is None and got[2] is None
+    with pytest.raises(NotImplementedError):
+        batched_inference(sf, None, cfg, default_args(sample_batches=True), _fake_predict)
+
+
+def test_shard_bounds_cover_all_rows():
+    for n in (0, 1, 7, 50257, 50304, 262144):
+        for world in (1, 2, 3, 8):
+            seen = 0
+            for r in range(world):
+                lo, hi, per = parallel.shard_bounds(n, world, r)
+                assert 0 <= lo <= hi <= n and hi - lo <= per
+                assert lo == min(n, r * per)
+                seen += hi - lo
+            assert seen == n and per * world >= n
+    assert parallel.packed_width(4096, True) == 8196 and parallel.packed_width(768, False) == 772
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rows, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = synthetic.make_config("tiny")
+    weights = synthetic.make_weights(cfg, seed=11)
+    src = synthetic.make_source_embeddings(cfg, seed=12)
+    sf = synthetic.make_random_surface_forms(cfg, n_rows, seed=21)
+    D = cfg.n_embd
+
+    def compute(lo, hi, block):  # the oracle stands in for the kernels; the packing / gather logic is what is tested
+        a, b, c = ho.hypernet_forward(cfg, weights, sf[lo:hi], src)
+        block[: hi - lo, :D] = torch.from_numpy(a)
+        block[: hi - lo, D:2 * D] = torch.from_numpy(b)
+        block[: hi - lo, 2 * D] = torch.from_numpy(c)
+
+    pin, pout, pbias = parallel.predict_sharded(n_rows, D, True, compute, torch.device("cpu"))
+    ret[rank] = (pin.numpy().copy(), pout.numpy().copy(), pbias.numpy().copy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows", [101, 64])
+def test_row_sharded_two_ranks_gloo(n_rows):
+    """world_size 2 over gloo: the sharded result equals the single-process result bit for bit on both ranks."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_rows, ret), nprocs=world, join=True)
+    cfg = synthetic.make_config("tiny")
+    want = ho.hypernet_forward(cfg, synthetic.make_weights(cfg, seed=11), synthetic.make_random_surface_forms(cfg, n_rows, seed=21),
+                               synthetic.make_source_embeddings(cfg, seed=12))
+    for rank in range(world):
+        for g, w in zip(ret[rank], want):
+            assert g.shape == w.shape
+            # each rank computes its rows in a smaller batch; fp32 GEMM blocking may differ in the last bit
+            np.testing.assert_allclose(g, w, rtol=0, atol=5e-6)
+    for a, b in zip(ret[0], ret[1]):
+        np.testing.assert_array_equal(a, b)

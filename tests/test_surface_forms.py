@@ -1,0 +1,124 @@
+"""Native retokenizer (C ABI, host code) against the reference-minted goldens, the Python oracle and the HF
+``tokenizers`` wheel; bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import retok_oracle as ro
+from zett_b200 import synthetic
+from zett_b200.surface_forms import NativeTokenizerModel, get_surface_form_matrix
+
+INT_CASES = ["unigram", "bpe", "bpe_fuse_ignore"]
+
+
+def native_model(spec):
+    if spec["type"] == "unigram":
+        return NativeTokenizerModel.unigram(list(zip(spec["vocab"], spec["scores"])), spec["unk_id"], spec["byte_fallback"])
+    return NativeTokenizerModel.bpe({t: i for i, t in enumerate(spec["vocab"])}, [tuple(m) for m in spec["merges"]],
+                                    unk_token=spec["unk_token"], fuse_unk=spec["fuse_unk"],
+                                    byte_fallback=spec["byte_fallback"], ignore_merges=spec["ignore_merges"])
+
+
+@pytest.mark.parametrize("case", INT_CASES)
+@pytest.mark.parametrize("threads", [1, 5])
+def test_native_matches_reference_goldens(golden_dir, case, threads):
+    g = np.load(os.path.join(golden_dir, f"surface_forms_{case}.npz"))
+    spec, tokens = json.loads(str(g["spec"])), json.loads(str(g["tokens"]))
+    sp = np.array([spec["special_tokens"].get(t, -1) for t in tokens], dtype=np.int32)
+    out, n_trunc = native_model(spec).surface_forms(tokens, int(g["maxlen"]), spec["pad_token_id"], sp, int(g["padding"]),
+                                                    n_threads=threads)
+    assert out.dtype == np.int32
+    np.testing.assert_array_equal(out, g["matrix"])
+    assert n_trunc == int(g["n_truncated"])
+
+
+@pytest.mark.parametrize("kind", ["unigram", "bpe"])
+def test_public_function_matches_hf_loop(kind):
+    """get_surface_form_matrix(tokens, maxlen, hn_tokenizer) == the reference's loop over the HF wheel."""
+    hn = synthetic.make_hn_tokenizer(kind, 3000, seed=3)
+    tokens = synthetic.make_target_tokens(4000, seed=4, specials=("</s>", "<unk>"))
+    got, nt = get_surface_form_matrix(tokens, 7, hn, padding=3)
+    want, nt2 = ro.surface_form_matrix_hf(tokens, 7, hn, padding=3)
+    np.testing.assert_array_equal(got, want)
+    assert nt == nt2 and got.shape == (4003, 7)
+    assert (got[-3:] == hn.pad_token_id).all()
+    assert got[0, 0] == hn.convert_tokens_to_ids("</s>") and (got[0, 1:] == hn.pad_token_id).all()
+
+
+def test_tokenize_randomised_against_hf_and_oracle():
+    from tokenizers import models
+    rng = np.random.default_rng(11)
+    alphabet = ["a", "b", "c", "Ġ", "é", "ł"]
+    for trial in range(25):
+        pieces = {"<unk>": 0.0}
+        for _ in range(int(rng.integers(5, 40))):
+            n = int(rng.integers(1, 5))
+            pieces["".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet) - 1, size=n))] = float(-rng.integers(1, 6))
+        vocab = list(pieces.items())
+        hf = models.Unigram(vocab, unk_id=0, byte_fallback=False)
+        nat = NativeTokenizerModel.unigram(vocab, 0)
+        orc = ro.UnigramOracle(vocab, 0)
+        for _ in range(200):
+            s = "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), size=int(rng.integers(0, 12))))
+            want = [t.id for t in hf.tokenize(s)] if s else []
+            assert nat.tokenize(s) == want == orc.tokenize(s), (vocab, s)
+
+
+def test_bpe_randomised_against_hf():
+    from tokenizers import models
+    rng = np.random.default_rng(12)
+    alphabet = ["a", "b", "c", "d", "é"]
+    for trial in range(20):
+        vocab = {"<unk>": 0}
+        for ch in alphabet[:-1] if trial % 2 else alphabet:
+            vocab[ch] = len(vocab)
+        merges = []
+        syms = [s for s in vocab if s != "<unk>"]
+        for _ in range(int(rng.integers(3, 25))):
+            a, b = syms[int(rng.integers(0, len(syms)))], syms[int(rng.integers(0, len(syms)))]
+            if (a, b) in merges:
+                continue
+            merges.append((a, b))
+            if a + b not in vocab:
+                vocab[a + b] = len(vocab)
+                syms.append(a + b)
+        for fuse in (False, True):
+            hf = models.BPE(vocab=vocab, merges=merges, unk_token="<unk>", fuse_unk=fuse)
+            nat = NativeTokenizerModel.bpe(vocab, merges, unk_token="<unk>", fuse_unk=fuse)
+            for _ in range(150):
+                s = "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), size=int(rng.integers(0, 14))))
+                want = [t.id for t in hf.tokenize(s)] if s else []
+                assert nat.tokenize(s) == want, (vocab, merges, fuse, s)
+
+
+def test_key_error_and_missing_unk():
+    hn = synthetic.make_hn_tokenizer("unigram", 600, seed=3)
+    with pytest.raises(KeyError):
+        get_surface_form_matrix(["ab c"], 7, hn)       # a raw space is not in the byte alphabet (utils.py:675)
+    with pytest.raises(KeyError):
+        get_surface_form_matrix(["ok", "日本"], 7, hn)
+    nat = NativeTokenizerModel.unigram([("a", -1.0), ("b", -2.0)], None)
+    assert nat.tokenize("ab") == [0, 1]
+    with pytest.raises(Exception):
+        nat.tokenize("abz")
+
+
+def test_empty_and_ragged_inputs():
+    hn = synthetic.make_hn_tokenizer("unigram", 600, seed=3)
+    out, nt = get_surface_form_matrix([], 7, hn, padding=2)
+    assert out.shape == (2, 7) and nt == 0 and (out == hn.pad_token_id).all()
+    out, nt = get_surface_form_matrix(["", "a", "a" * 40], 5, hn)
+    want, nt2 = ro.surface_form_matrix_hf(["", "a", "a" * 40], 5, hn)
+    np.testing.assert_array_equal(out, want)
+    assert nt == nt2 == 1
+
+
+def test_tokenizer_object_input():
+    """First argument may be a tokenizer: rows follow convert_ids_to_tokens(range(len(tokenizer))) (utils.py:655-659)."""
+    hn = synthetic.make_hn_tokenizer("unigram", 600, seed=3)
+    target = synthetic.make_hn_tokenizer("unigram", 500, seed=9)
+    got, _ = get_surface_form_matrix(target, 7, hn)
+    want, _ = ro.surface_form_matrix_hf(target.convert_ids_to_tokens(range(len(target))), 7, hn)
+    np.testing.assert_array_equal(got, want)
