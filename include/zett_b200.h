@@ -122,6 +122,7 @@ typedef struct zett_hn_stats {
   double flops_executed;       /* algorithmic FLOPs of the GEMMs actually issued (one count per product term set)  */
   double gemm_ms;              /* summed CUDA-event time of the GEMM kernel launches (only with zett_hn_set_timing) */
   int64_t gemm_launches;
+  int64_t distinct_ids;        /* distinct surface-form ids summed over the passes (input projection runs per id)  */
 } zett_hn_stats;
 int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out);
 

@@ -92,3 +92,20 @@ def test_row_sharded_two_ranks_gloo(n_rows):
             np.testing.assert_allclose(g, w, rtol=0, atol=5e-6)
     for a, b in zip(ret[0], ret[1]):
         np.testing.assert_array_equal(a, b)
+
+
+def test_checkpoint_roundtrip_and_automodel(tmp_path):
+    """Reference state_dict names in, save_pretrained / from_pretrained / AutoModel out (README.md:93-117 call surface)."""
+    import zett_b200
+    from transformers import AutoModel
+    from zett_b200.modeling_hypernet import ZettHypernet, load_weights_numpy
+    cfg = synthetic.make_config("tiny_lang")
+    weights = synthetic.make_weights(cfg, seed=11)
+    model = load_weights_numpy(ZettHypernet(cfg), weights)
+    assert set(model.state_dict()) == set(weights)
+    model.save_pretrained(tmp_path)
+    zett_b200.register_auto_classes()
+    again = AutoModel.from_pretrained(tmp_path)
+    assert isinstance(again, ZettHypernet) and again.config.hn_embed_lang_id and again.config.n_langs == 5
+    for k, v in again.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), weights[k])

@@ -16,6 +16,9 @@ def __getattr__(name):  # torch-dependent parts load lazily so that the config /
     if name == "ZettHypernet":
         from .modeling_hypernet import ZettHypernet
         return ZettHypernet
+    if name == "register_auto_classes":
+        from .modeling_hypernet import register_auto_classes
+        return register_auto_classes
     if name == "get_surface_form_matrix":
         from .surface_forms import get_surface_form_matrix
         return get_surface_form_matrix

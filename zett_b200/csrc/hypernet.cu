@@ -313,7 +313,9 @@ struct Workspace {
   size_t bytes = 0;
   // pack metadata
   int *counts_all = nullptr, *row_start1 = nullptr, *row_start2 = nullptr, *tok_src = nullptr, *tok_pos = nullptr,
-      *tok_enc = nullptr, *tok1_row = nullptr, *lang_enc = nullptr, *tok2_row = nullptr;
+      *tok_enc = nullptr, *tok1_row = nullptr, *lang_enc = nullptr, *tok2_row = nullptr, *id_claim = nullptr,
+      *id_slot = nullptr, *uniq_src = nullptr, *tok_u = nullptr;
+  long long uniq_cap = 0;
   unsigned char* tok2_valid = nullptr;
   // position-indexed buffers
   uint16_t *P_E = nullptr, *PH_a = nullptr, *PH_b = nullptr, *PI = nullptr;
@@ -346,7 +348,7 @@ struct zett_hn {
   // statistics
   long long passes = 0;
   zett_hn_stats stats{};
-  double coef_t1 = 0, coef_t2 = 0, coef_rows = 0;  // FLOPs per surface position / encoder position / row
+  double coef_t1 = 0, coef_t2 = 0, coef_rows = 0, coef_u = 0;  // FLOPs per surface position / encoder position / row / distinct id
 };
 
 namespace {
@@ -374,8 +376,9 @@ size_t workspace_bytes_for(const zett_hn* h, long long rows) {
   const long long t1 = rows * h->L, t2 = rows * h->S;
   const long long H = h->H, I = h->I, E = h->E;
   size_t b = 0;
-  b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 4 * t1 + rows + t2) + t2;
-  b += 2ull * 2 * t1 * E;                 // P_E
+  const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
+  b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 6 * t1 + rows + t2 + 2 * n_ids) + t2;
+  b += 2ull * 2 * std::min<long long>(t1, n_ids) * E;  // P_E
   b += 2ull * 2 * t2 * H * 2;             // PH_a, PH_b
   b += 2ull * 2 * t2 * I;                 // PI
   b += 4ull * t2 * H * 3 + 4ull * t2 * 3 * H;  // F1..F3, F4
@@ -400,7 +403,13 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.lang_enc, rows);
   WS_ALLOC(w.tok2_row, t2);
   WS_ALLOC(w.tok2_valid, t2);
-  WS_ALLOC(w.P_E, 2 * t1 * E);
+  const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
+  w.uniq_cap = std::min<long long>(t1, n_ids);
+  WS_ALLOC(w.id_claim, n_ids);
+  WS_ALLOC(w.id_slot, n_ids);
+  WS_ALLOC(w.uniq_src, w.uniq_cap);
+  WS_ALLOC(w.tok_u, t1);
+  WS_ALLOC(w.P_E, 2 * w.uniq_cap * E);
   WS_ALLOC(w.PH_a, 2 * t2 * H);
   WS_ALLOC(w.PH_b, 2 * t2 * H);
   WS_ALLOC(w.PI, 2 * t2 * I);
@@ -519,7 +528,9 @@ int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
   return ZETT_OK;
 }
 
-enum MClass { kMSurface, kMEncoder, kMRows };
+enum MClass { kMSurface, kMEncoder, kMRows, kMUnique };
+
+int count_slot(MClass m) { return m == kMSurface ? kCntSurface : (m == kMEncoder ? kCntEncoder : kCntUnique); }
 
 // One Linear layer through the GEMM engine.  `a` / `out_*` are plane-0 pointers; `cap` = rows the buffers hold.
 int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const uint16_t* a, long long cap, MClass mclass,
@@ -530,7 +541,7 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   g.w = w.planes + static_cast<long long>(row_off) * w.k; g.w_plane_stride = w.plane_stride();
   g.n = n_rows_w; g.k = w.k;
   if (mclass == kMRows) { g.m_host = m_rows; g.m_dev = nullptr; }
-  else { g.m_host = static_cast<int>(cap); g.m_dev = counts + (mclass == kMSurface ? kCntSurface : kCntEncoder); }
+  else { g.m_host = static_cast<int>(cap); g.m_dev = counts + count_slot(mclass); }
   g.ep.bias = w.bias + row_off;
   g.ep.act = act;
   g.ep.col_scale = col_scale; g.ep.col_shift = col_shift;
@@ -538,7 +549,8 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   g.ep.out_p0 = out_p0; g.ep.out_p1 = out_p0 ? plane1(out_p0, out_cap * n_rows_w, h) : nullptr; g.ep.ld_split = n_rows_w;
   g.ep.split_fmt = h->gemm.split_fmt;
   const double f = 2.0 * n_rows_w * w.k;
-  if (mclass == kMSurface) h->coef_t1 += f; else if (mclass == kMEncoder) h->coef_t2 += f; else h->coef_rows += f;
+  if (mclass == kMSurface) h->coef_t1 += f; else if (mclass == kMEncoder) h->coef_t2 += f;
+  else if (mclass == kMUnique) h->coef_u += f; else h->coef_rows += f;
   return h->gemm.launch(g, stream);
 }
 
@@ -552,7 +564,7 @@ int run_projector(zett_hn* h, const Projector& pb, const uint16_t* xp, const flo
   ln_out.a = z; ln_out.lda = h->H; ln_out.res = xf;
   ln_out.gamma = pb.ln_w; ln_out.beta = pb.ln_b; ln_out.eps = 1e-6f;
   if (mclass == kMRows) { ln_out.n_dev = nullptr; ln_out.n_host = m_rows; }
-  else { ln_out.n_dev = counts + (mclass == kMSurface ? kCntSurface : kCntEncoder); ln_out.n_host = 0; }
+  else { ln_out.n_dev = counts + count_slot(mclass); ln_out.n_host = 0; }
   return launch_ln(h, ln_out, mclass == kMRows ? m_rows : cap, stream);
 }
 
@@ -566,15 +578,18 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
   const int n_layers = h->cfg.hn_n_layers;
   int* counts = w.counts_all + (h->passes % kMaxPassSlots) * kCntSlots;
   const int fmt = h->gemm.split_fmt;
-  h->coef_t1 = h->coef_t2 = h->coef_rows = 0;
+  h->coef_t1 = h->coef_t2 = h->coef_rows = h->coef_u = 0;
+  const long long capu = w.uniq_cap;
 
   // ---- pack ------------------------------------------------------------------------------------------------------
   ZETT_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * kCntSlots, stream));
+  ZETT_CUDA(cudaMemsetAsync(w.id_claim, 0x7F, sizeof(int) * (static_cast<size_t>(h->cfg.original_vocab_size) + h->n_fallback), stream));
   PackParams pp{};
   pp.ids = ids; pp.n_rows = rows; pp.L = L; pp.pad_id = h->cfg.pad_token_id; pp.v0 = h->cfg.original_vocab_size;
   pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.counts = counts;
   pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_src = w.tok_src; pp.tok_pos = w.tok_pos;
   pp.tok_enc = w.tok_enc; pp.tok1_row = w.tok1_row; pp.lang_enc = w.lang_enc; pp.tok2_row = w.tok2_row; pp.tok2_valid = w.tok2_valid;
+  pp.id_claim = w.id_claim; pp.id_slot = w.id_slot; pp.uniq_src = w.uniq_src; pp.tok_u = w.tok_u;
   pack_rows_kernel<<<1, kPackThreads, 0, stream>>>(pp);
   ZETT_CUDA(cudaGetLastError());
   ++h->gemm.launches;
@@ -583,29 +598,30 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
   {
     GatherParams gp{};
     gp.source = source; gp.v0_rows = v0_rows; gp.fallback = h->fallback;
-    gp.scale_w = h->in_scale_w; gp.scale_b = h->in_scale_b; gp.tok_src = w.tok_src; gp.n_tok = counts + kCntSurface;
-    gp.E = E; gp.split_fmt = fmt; gp.out_p0 = w.P_E; gp.out_p1 = plane1(w.P_E, cap1 * E, h);
+    gp.scale_w = h->in_scale_w; gp.scale_b = h->in_scale_b; gp.tok_src = w.uniq_src; gp.n_tok = counts + kCntUnique;
+    gp.E = E; gp.split_fmt = fmt; gp.out_p0 = w.P_E; gp.out_p1 = plane1(w.P_E, capu * E, h);
     const size_t smem = 2ull * E * 4;
     const int per_sm = std::max<int>(1, std::min<int>(8, 200 * 1024 / static_cast<int>(smem + 64)));
-    const int grid = static_cast<int>(std::min<long long>(static_cast<long long>(rows) * L, 148LL * per_sm));
+    const int grid = static_cast<int>(std::min<long long>(std::min<long long>(static_cast<long long>(rows) * L, capu), 148LL * per_sm));
     gather_rescale_kernel<<<grid, kGatherThreads, smem, stream>>>(gp);
     ZETT_CUDA(cudaGetLastError());
     ++h->gemm.launches;
   }
 
   // ---- input_projection = Linear(E, H); ProjectorBlock  (modeling_hypernet.py:100-110,189) -----------------------
-  ZETT_TRY(run_linear(h, h->in_proj0, 0, H, w.P_E, cap1, kMSurface, 0, counts, kActNone, w.F1, H, w.PH_a, cap1, nullptr,
+  // evaluated once per distinct id of the pass (the result depends on the id only); positions pick their row below
+  ZETT_TRY(run_linear(h, h->in_proj0, 0, H, w.P_E, capu, kMUnique, 0, counts, kActNone, w.F1, H, w.PH_a, capu, nullptr,
                       nullptr, stream));
   {
     LnParams ln{};  // U = LN_1e-6(gelu(dense2(gelu(dense1 y))) + y), in place over Z
     ln.out_f32 = w.F2;
-    ZETT_TRY(run_projector(h, h->in_proj1, w.PH_a, w.F1, cap1, kMSurface, 0, counts, w.PI, w.F2, ln, stream));
+    ZETT_TRY(run_projector(h, h->in_proj1, w.PH_a, w.F1, capu, kMUnique, 0, counts, w.PI, w.F2, ln, stream));
   }
   // ---- RobertaEmbeddings: + token_type[0] + position[pos]; LayerNorm 1e-5; scatter into the encoder packing -------
   const bool single_layer = n_layers == 1;
   {
     LnParams ln{};
-    ln.a = w.F2; ln.lda = H; ln.vec0 = h->type0; ln.table = h->pos_table; ln.table_idx = w.tok_pos;
+    ln.a = w.F2; ln.lda = H; ln.in_index = w.tok_u; ln.vec0 = h->type0; ln.table = h->pos_table; ln.table_idx = w.tok_pos;
     ln.gamma = h->emb_ln_w; ln.beta = h->emb_ln_b; ln.eps = h->cfg.encoder_layer_norm_eps;
     ln.n_dev = counts + kCntSurface; ln.out_index = w.tok_enc;
     ln.out_f32 = w.F3; ln.out_p0 = w.PH_a; ln.out_p1 = plane1(w.PH_a, cap2 * H, h);
@@ -941,18 +957,20 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
     const long long n_pass = std::min<long long>(-h->stats.packed_positions, kMaxPassSlots);
     std::vector<int> host(static_cast<size_t>(kMaxPassSlots) * kCntSlots);
     ZETT_CUDA(cudaMemcpy(host.data(), h->ws.counts_all, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
-    long long t1 = 0, t2 = 0, rows = 0;
+    long long t1 = 0, t2 = 0, rows = 0, uq = 0;
     int bad = 0;
     for (long long i = 0; i < n_pass; ++i) {
       const long long slot = ((h->passes - 1 - i) % kMaxPassSlots + kMaxPassSlots) % kMaxPassSlots;
       t1 += host[slot * kCntSlots + kCntSurface];
       t2 += host[slot * kCntSlots + kCntEncoder];
       rows += host[slot * kCntSlots + kCntRows];
+      uq += host[slot * kCntSlots + kCntUnique];
       bad |= host[slot * kCntSlots + kCntBadId];
     }
     h->stats.packed_positions = t1;
     h->stats.encoder_positions = t2;
-    h->stats.flops_executed = h->coef_t1 * t1 + h->coef_t2 * t2 + h->coef_rows * rows;
+    h->stats.flops_executed = h->coef_t1 * t1 + h->coef_t2 * t2 + h->coef_rows * rows + h->coef_u * uq;
+    h->stats.distinct_ids = uq;
     if (bad)
       return fail(ZETT_ERR_INDEX, "surface-form id outside [0, original_vocab_size + max(hn_n_extra_tokens, 1))");
   }

@@ -25,7 +25,7 @@ constexpr int kPackThreads = 1024;
 constexpr int kMaxSurfaceLen = 32;
 
 // counts[] slots
-enum : int { kCntSurface = 0, kCntEncoder = 1, kCntBadId = 2, kCntRows = 3, kCntSlots = 8 };
+enum : int { kCntSurface = 0, kCntEncoder = 1, kCntBadId = 2, kCntRows = 3, kCntUnique = 4, kCntSlots = 8 };
 
 struct PackParams {
   const int32_t* ids;    // [n_rows, L]
@@ -42,6 +42,12 @@ struct PackParams {
   int* lang_enc;               // [n_rows] index of the lang slot in the encoder packing (lang_slot only)
   int* tok2_row;               // [T2]
   unsigned char* tok2_valid;   // [T2]  1 = usable as attention key
+  // de-duplication of the input projection: it depends on the id only (positions are added after it), so it is
+  // evaluated once per DISTINCT id of the pass
+  int* id_claim;               // [v0 + n_fallback] scratch, preset to INT_MAX-like: lowest position holding the id
+  int* id_slot;                // [v0 + n_fallback] scratch: index of the id among the distinct ids
+  int* uniq_src;               // [U]   tok_src code of each distinct id, in order of first occurrence
+  int* tok_u;                  // [T1]  index into the distinct ids
 };
 
 __device__ __forceinline__ uint32_t kept_mask(const int32_t* row, int L, int pad_id, int lang_slot, uint32_t& nonpad) {
@@ -111,7 +117,8 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_rows_kernel(const PackPa
       if (!((kept >> q) & 1u)) continue;
       int id = row[q];
       id = max(0, min(id, id_limit - 1));  // never read out of bounds; kCntBadId reports the violation
-      p.tok_src[t1 + j] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
+      p.tok_src[t1 + j] = id;  // provisional: the id itself, recoded below
+      atomicMin(&p.id_claim[id], t1 + j);
       p.tok_pos[t1 + j] = q;
       p.tok_enc[t1 + j] = t2_base + j;
       p.tok1_row[t1 + j] = r;
@@ -126,6 +133,40 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_rows_kernel(const PackPa
     }
     t1 += j;
   }
+  // ---- distinct ids: owner = lowest position of each id; owners are numbered in position order -------------------
+  const int t_begin = warp_sums2[warp] + incl - local, t_end = t_begin + local;
+  __syncthreads();
+  int owners = 0;
+  for (int t = t_begin; t < t_end; ++t) owners += (__ldcg(&p.id_claim[p.tok_src[t]]) == t) ? 1 : 0;
+  int oincl = owners;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, oincl, o);
+    if (lane >= o) oincl += v;
+  }
+  if (lane == 31) warp_sums[warp] = oincl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = warp_sums[lane];
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_sums2[lane] = wi - w;
+    if (lane == 31) p.counts[kCntUnique] = wi;
+  }
+  __syncthreads();
+  int u = warp_sums2[warp] + oincl - owners;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int id = p.tok_src[t];
+    if (__ldcg(&p.id_claim[id]) == t) {
+      p.id_slot[id] = u;
+      p.uniq_src[u] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
+      ++u;
+    }
+  }
+  __syncthreads();
+  for (int t = t_begin; t < t_end; ++t) p.tok_u[t] = __ldcg(&p.id_slot[p.tok_src[t]]);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -234,6 +275,7 @@ constexpr int kLnMaxVec = 8;  // float4 per thread: H <= 4 * 8 * blockDim
 struct LnParams {
   const float* a;
   long long lda;             // 0 broadcasts one vector to every row
+  const int* in_index;       // nullable: row of `a` to read for position t (distinct-id table -> positions)
   const float* res;          // nullable, row stride H
   const float* vec0;         // nullable [H]
   const float* table;        // nullable [*, H]
@@ -293,7 +335,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const int H4 = p.H >> 2;
   for (int t = blockIdx.x; t < n; t += gridDim.x) {
     float4 v[kLnMaxVec];
-    const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(t) * p.lda);
+    const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(p.in_index ? __ldg(p.in_index + t) : t) * p.lda);
     const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res + static_cast<long long>(t) * p.H) : nullptr;
     const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) : nullptr;
     const float4* e4 = nullptr;

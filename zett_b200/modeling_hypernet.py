@@ -270,3 +270,13 @@ def load_weights_numpy(model: ZettHypernet, weights: Dict[str, np.ndarray]):
     if unexpected or missing:
         raise ValueError("state_dict mismatch: missing=%s unexpected=%s" % (missing, unexpected))
     return model
+
+
+def register_auto_classes():
+    """``AutoConfig`` / ``AutoModel`` resolve ``model_type == "zett_hypernetwork"`` to the B200 classes, so
+    ``AutoModel.from_pretrained(path)`` (README.md:93-117 of the reference) returns a ``zett_b200.ZettHypernet``.
+    With ``trust_remote_code=True`` and an ``auto_map`` in the checkpoint HF prefers the checkpoint's own code; pass
+    ``trust_remote_code=False`` (or use ``ZettHypernet.from_pretrained``) to take this implementation."""
+    from transformers import AutoConfig, AutoModel
+    AutoConfig.register(ZettHypernetConfig.model_type, ZettHypernetConfig, exist_ok=True)
+    AutoModel.register(ZettHypernetConfig, ZettHypernet, exist_ok=True)
