@@ -73,7 +73,9 @@ typedef struct zett_hn_config {
   int32_t max_rows_per_pass;               /* rows handled by one pass of the kernels (0 -> 16384, transfer.py:44) */
   int32_t gemm_impl;                       /* 0 = auto (tcgen05 2-CTA), 1 = tcgen05 1-CTA, 2 = tcgen05 2-CTA,
                                               3 = SIMT fp32 debug kernel (checker, never the default)              */
-  int32_t split_terms;                     /* 0/3 = 3-term bf16 split (fp32-class accuracy), 1 = single bf16 pass  */
+  int32_t split_terms;                     /* operand precision: 0/3 = three bf16 MMA terms (A0W0 + A1W0 + A0W1),
+                                              2 = fp16 MMA + two e5m2 correction MMAs at fp8 rate, 1 = one bf16 pass
+                                              (1 misses the 1e-3 parity budget; for comparison only)               */
 } zett_hn_config;
 
 typedef struct zett_hn zett_hn;

@@ -5,12 +5,22 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cstdint>
 
 namespace zett {
 
 enum Act : int { kActNone = 0, kActGeluTanh = 1, kActGeluErf = 2 };
-enum SplitFmt : int { kFmtBf16 = 0, kFmtFp16 = 1 };
+// Operand formats of the GEMM engine.  An operand x is stored as planes whose products restore ~fp32 accuracy:
+//   kFmtBf16 / kFmtFp16 : p0 = round16(x), p1 = round16(x - p0);        A.W ~= A0 W0 + A1 W0 + A0 W1      (3 f16-kind MMAs)
+//   kFmtF16F8           : p0 = fp16(x) and two e5m2 planes that carry the first-order corrections at fp8 rate
+//                           activations: q0 = e5m2(2^6 (x - p0)),  q1 = e5m2(2^-6 x)
+//                           weights    : q0 = e5m2(2^-6 w),        q1 = e5m2(2^6 (w - p0))
+//                         A.W ~= A0 W0 (f16 MMA) + Aq0 Wq0 + Aq1 Wq1 (two f8f6f4 MMAs, half the cost each);
+//                         the 2^+-6 factors cancel inside each product and keep both fp8 operands in e5m2's normal range.
+//   The two fp8 planes live where plane 1 lives (same 2 bytes per element): q0 = (uint8*)p1, q1 = q0 + (p1 - p0).
+enum SplitFmt : int { kFmtBf16 = 0, kFmtFp16 = 1, kFmtF16F8 = 2 };
+constexpr float kF8Up = 64.0f, kF8Down = 0.015625f;
 
 struct EpilogueParams {
   const float* bias;        // [n] or nullptr
@@ -35,6 +45,108 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 // exact GELU, hidden_act="gelu" of the RoBERTa encoder
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+}
+
+// kFmtF16F8: returns p0 (fp16 bits) and the two e5m2 bytes
+__device__ __forceinline__ void split_f16f8(float x, bool is_weight, uint16_t& p0, uint8_t& q0, uint8_t& q1) {
+  const float xc = fminf(fmaxf(x, -65504.f), 65504.f);
+  const __half h = __float2half_rn(xc);
+  const float lo = x - __half2float(h);
+  p0 = __half_as_ushort(h);
+  if (is_weight) {
+    q0 = __nv_cvt_float_to_fp8(x * kF8Down, __NV_SATFINITE, __NV_E5M2);
+    q1 = __nv_cvt_float_to_fp8(lo * kF8Up, __NV_SATFINITE, __NV_E5M2);
+  } else {
+    q0 = __nv_cvt_float_to_fp8(lo * kF8Up, __NV_SATFINITE, __NV_E5M2);
+    q1 = __nv_cvt_float_to_fp8(x * kF8Down, __NV_SATFINITE, __NV_E5M2);
+  }
+}
+
+__device__ __forceinline__ float e5m2_to_float(uint8_t v) {
+  const __half_raw hr = __nv_cvt_fp8_to_halfraw(v, __NV_E5M2);
+  return __half2float(__half(hr));
+}
+
+__device__ __forceinline__ uint32_t pack4_u8(const uint8_t* b) {
+  return uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16) | (uint32_t(b[3]) << 24);
+}
+
+// Store 4 consecutive elements (offset `off`, a multiple of 4) of an operand in format `fmt`.
+__device__ __forceinline__ void store_operand4(uint16_t* p0, uint16_t* p1, long long off, const float* y, int fmt, bool is_weight) {
+  if (fmt == kFmtF16F8) {
+    uint16_t a[4];
+    uint8_t b[4], c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_f16f8(y[i], is_weight, a[i], b[i], c[i]);
+    uint2 pa;
+    pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
+    *reinterpret_cast<uint2*>(p0 + off) = pa;
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1);
+    uint8_t* q1 = q0 + (p1 - p0);
+    *reinterpret_cast<uint32_t*>(q0 + off) = pack4_u8(b);
+    *reinterpret_cast<uint32_t*>(q1 + off) = pack4_u8(c);
+  } else {
+    uint16_t a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (fmt == kFmtBf16) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(y[i]);
+        a[i] = __bfloat16_as_ushort(h);
+        b[i] = __bfloat16_as_ushort(__float2bfloat16_rn(y[i] - __bfloat162float(h)));
+      } else {
+        const __half h = __float2half_rn(y[i]);
+        a[i] = __half_as_ushort(h);
+        b[i] = __half_as_ushort(__float2half_rn(y[i] - __half2float(h)));
+      }
+    }
+    uint2 pa, pb;
+    pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
+    pb.x = b[0] | (uint32_t(b[1]) << 16); pb.y = b[2] | (uint32_t(b[3]) << 16);
+    *reinterpret_cast<uint2*>(p0 + off) = pa;
+    if (p1) *reinterpret_cast<uint2*>(p1 + off) = pb;
+  }
+}
+
+// 8 consecutive elements (offset a multiple of 8): 16-byte stores for the 16-bit planes, 8-byte for the fp8 planes
+__device__ __forceinline__ void store_operand8(uint16_t* p0, uint16_t* p1, long long off, const float* y, int fmt, bool is_weight) {
+  if (fmt == kFmtF16F8) {
+    uint16_t a[8];
+    uint8_t b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_f16f8(y[i], is_weight, a[i], b[i], c[i]);
+    uint4 pa;
+    pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
+    pa.z = a[4] | (uint32_t(a[5]) << 16); pa.w = a[6] | (uint32_t(a[7]) << 16);
+    *reinterpret_cast<uint4*>(p0 + off) = pa;
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1);
+    uint8_t* q1 = q0 + (p1 - p0);
+    *reinterpret_cast<uint2*>(q0 + off) = make_uint2(pack4_u8(b), pack4_u8(b + 4));
+    *reinterpret_cast<uint2*>(q1 + off) = make_uint2(pack4_u8(c), pack4_u8(c + 4));
+  } else {
+    store_operand4(p0, p1, off, y, fmt, is_weight);
+    store_operand4(p0, p1, off + 4, y + 4, fmt, is_weight);
+  }
+}
+
+// one element (attention output, ragged tails)
+__device__ __forceinline__ void store_operand1(uint16_t* p0, uint16_t* p1, long long off, float y, int fmt) {
+  if (fmt == kFmtF16F8) {
+    uint16_t a;
+    uint8_t b, c;
+    split_f16f8(y, false, a, b, c);
+    p0[off] = a;
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1);
+    q0[off] = b;
+    (q0 + (p1 - p0))[off] = c;
+  } else if (fmt == kFmtBf16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(y);
+    p0[off] = __bfloat16_as_ushort(h);
+    if (p1) p1[off] = __bfloat16_as_ushort(__float2bfloat16_rn(y - __bfloat162float(h)));
+  } else {
+    const __half h = __float2half_rn(y);
+    p0[off] = __half_as_ushort(h);
+    if (p1) p1[off] = __half_as_ushort(__float2half_rn(y - __half2float(h)));
+  }
 }
 
 __device__ __forceinline__ void split16(float x, int fmt, uint16_t& p0, uint16_t& p1) {
@@ -91,29 +203,12 @@ __device__ __forceinline__ void epilogue_store32(const EpilogueParams& ep, int r
     }
   }
   if (ep.out_p0) {
-    uint16_t* o0 = ep.out_p0 + static_cast<long long>(row) * ep.ld_split + col0;
-    uint16_t* o1 = ep.out_p1 ? ep.out_p1 + static_cast<long long>(row) * ep.ld_split + col0 : nullptr;
+    const long long off = static_cast<long long>(row) * ep.ld_split + col0;
     if (ncols == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint16_t a[8], b[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) split16(v[j + t], ep.split_fmt, a[t], b[t]);
-        uint4 pa, pb;
-        pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
-        pa.z = a[4] | (uint32_t(a[5]) << 16); pa.w = a[6] | (uint32_t(a[7]) << 16);
-        pb.x = b[0] | (uint32_t(b[1]) << 16); pb.y = b[2] | (uint32_t(b[3]) << 16);
-        pb.z = b[4] | (uint32_t(b[5]) << 16); pb.w = b[6] | (uint32_t(b[7]) << 16);
-        *reinterpret_cast<uint4*>(o0 + j) = pa;
-        if (o1) *reinterpret_cast<uint4*>(o1 + j) = pb;
-      }
+      for (int j = 0; j < 32; j += 8) store_operand8(ep.out_p0, ep.out_p1, off + j, v + j, ep.split_fmt, false);
     } else {
-      for (int j = 0; j < ncols; ++j) {
-        uint16_t a, b;
-        split16(v[j], ep.split_fmt, a, b);
-        o0[j] = a;
-        if (o1) o1[j] = b;
-      }
+      for (int j = 0; j < ncols; ++j) store_operand1(ep.out_p0, ep.out_p1, off + j, v[j], ep.split_fmt);
     }
   }
 }

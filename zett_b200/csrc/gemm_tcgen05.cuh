@@ -32,10 +32,13 @@ struct GemmShape {
   int n, k;
   int block_n;         // 32, 64, 128 or 256
   int n_terms;         // 1 or 3
-  int n_planes;        // planes held by the tensor maps' boxes (1 or 2)
-  uint32_t idesc;      // tcgen05 instruction descriptor
+  int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
+  int f8;              // 1: operand format kFmtF16F8 -- one fp16 plane + two e5m2 correction planes (epilogue.cuh)
+  uint32_t idesc;      // tcgen05 instruction descriptor (kind::f16)
+  uint32_t idesc8;     // tcgen05 instruction descriptor (kind::f8f6f4), f8 only
   int num_stages;
-  uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;
+  uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;   // 16-bit planes: 128-byte rows
+  uint32_t a8_plane_bytes, b8_plane_bytes;              // fp8 planes: 64-byte rows
 };
 
 struct TileCoord { int m_blk, n_blk; };
@@ -55,6 +58,7 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_til
 template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_a8, const __grid_constant__ CUtensorMap tmap_b8,
                     const GemmShape s, const EpilogueParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -84,6 +88,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (s.f8) {
+      prefetch_tmap(&tmap_a8);
+      prefetch_tmap(&tmap_b8);
+    }
     for (int i = 0; i < s.num_stages; ++i) {
       mbar_init(full_bar(i), CG);   // one arrive(+tx) per producing CTA, all on the leader's barrier
       mbar_init(empty_bar(i), 1);   // one tcgen05.commit
@@ -114,15 +122,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
           const uint32_t a_dst = smem_base + stage * s.stage_bytes;
           const uint32_t b_dst = a_dst + s.n_planes * s.a_plane_bytes;
+          const uint32_t a8_dst = b_dst + s.n_planes * s.b_plane_bytes;
+          const uint32_t b8_dst = a8_dst + 2u * s.a8_plane_bytes;
           if constexpr (CG == 1) {
             mbar_expect_tx(full_bar(stage), s.stage_bytes);
             tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * kBlockK, row_a, 0);
             tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * kBlockK, row_b, 0);
+            if (s.f8) {
+              tma_load_3d(&tmap_a8, full_bar(stage), a8_dst, kb * kBlockK, row_a, 0);
+              tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * kBlockK, row_b, 0);
+            }
           } else {
             if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
             else mbar_arrive_cluster(full_bar(stage), 0);
             tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * kBlockK, row_a, 0);
             tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * kBlockK, row_b, 0);
+            if (s.f8) {
+              tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * kBlockK, row_a, 0);
+              tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * kBlockK, row_b, 0);
+            }
           }
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -151,9 +169,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
             const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
             umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
-            if (s.n_terms == 3) {
+            if (s.n_terms == 3 && !s.f8) {
               umma_f16<CG>(tmem_d, da1 + koff, db0 + koff, s.idesc, 1u);
               umma_f16<CG>(tmem_d, da0 + koff, db1 + koff, s.idesc, 1u);
+            }
+          }
+          if (s.f8) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
+            const uint32_t a8 = b0 + s.n_planes * s.b_plane_bytes;
+            const uint32_t b8 = a8 + 2u * s.a8_plane_bytes;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              const uint64_t dqa = umma_desc_sw64(a8 + pl * s.a8_plane_bytes), dqb = umma_desc_sw64(b8 + pl * s.b8_plane_bytes);
+#pragma unroll
+              for (int kk = 0; kk < kBlockK / 32; ++kk) umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, 1u);
             }
           }
           umma_commit<CG>(empty_bar(stage));                       // frees the smem stage (both CTAs)

@@ -87,6 +87,27 @@ int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long
   return ZETT_OK;
 }
 
+// 3-D map {K, rows, 2} over the two e5m2 correction planes, box {64, box_rows, 2}, 64-byte swizzle
+int make_plane8_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long k, long long plane_stride_bytes,
+                     int box_rows) {
+  EncodeTiledFn enc;
+  ZETT_TRY(get_encode_fn(&enc));
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), 2};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(plane_stride_bytes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (fp8 planes) failed (%d): rows=%lld k=%lld plane_stride=%lld box_rows=%d",
+             static_cast<int>(r), rows, k, plane_stride_bytes, box_rows);
+    return fail(ZETT_ERR_CUDA, buf);
+  }
+  return ZETT_OK;
+}
+
 struct DeviceInfo {
   int device = -1;
   int num_sms = 0;
@@ -141,6 +162,8 @@ struct GemmArgs {
   long long a_plane_stride = 0;    // elements between plane 0 and plane 1
   const uint16_t* w = nullptr;     // plane 0 of W, [n, k]
   long long w_plane_stride = 0;
+  const uint8_t* a_q = nullptr;    // kFmtF16F8: first fp8 plane of A / W (second one plane_stride bytes further)
+  const uint8_t* w_q = nullptr;
   int n = 0, k = 0;
   int m_host = 0;
   const int* m_dev = nullptr;
@@ -150,9 +173,13 @@ struct GemmArgs {
 struct GemmEngine {
   DeviceInfo dev;
   int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 2-CTA, 3: SIMT
-  int n_terms = 3;
+  int n_terms = 3;     // 3: 16-bit three-term split, 1: single 16-bit pass, 2: fp16 + two e5m2 correction passes
   int split_fmt = kFmtBf16;
   std::map<std::tuple<const void*, long long, long long, long long, int, int>, CUtensorMap> tmaps;
+  void set_precision(int terms) {
+    n_terms = (terms == 1 || terms == 2) ? terms : 3;
+    split_fmt = n_terms == 2 ? kFmtF16F8 : kFmtBf16;
+  }
   long long launches = 0;
   // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
   bool timing = false;
@@ -193,6 +220,17 @@ struct GemmEngine {
     *out = &it->second;
     return ZETT_OK;
   }
+  int tmap8(const uint8_t* base, long long rows, long long k, long long plane_stride, int box_rows, const CUtensorMap** out) {
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows, 8);
+    auto it = tmaps.find(key);
+    if (it == tmaps.end()) {
+      CUtensorMap m;
+      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, plane_stride, box_rows));
+      it = tmaps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return ZETT_OK;
+  }
 
   static int pick_block_n(int n) {
     for (int bn : {256, 128, 64, 32}) if (n % bn == 0) return bn;
@@ -203,10 +241,14 @@ struct GemmEngine {
     if (g.k % 8 != 0) return fail(ZETT_ERR_INVALID, "GEMM K must be a multiple of 8");
     ++launches;
     const int n_planes = n_terms == 3 ? 2 : 1;
+    const bool f8 = n_terms == 2;
+    if (f8 && (!g.a_q || !g.w_q)) return fail(ZETT_ERR_INVALID, "fp8 planes missing");
     if (impl == 3) {
       SimtGemmParams s{};
       s.a0 = g.a; s.a1 = n_planes == 2 ? g.a + g.a_plane_stride : nullptr;
       s.w0 = g.w; s.w1 = n_planes == 2 ? g.w + g.w_plane_stride : nullptr;
+      s.aq = f8 ? g.a_q : nullptr; s.aq_stride = g.a_plane_stride;
+      s.wq = f8 ? g.w_q : nullptr; s.wq_stride = g.w_plane_stride;
       s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k; s.split_fmt = split_fmt;
       dim3 grid((g.n + 31) / 32, (g.m_host + 127) / 128);
       if (grid.y == 0 || grid.x == 0) return ZETT_OK;
@@ -220,20 +262,28 @@ struct GemmEngine {
     GemmShape s{};
     s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
     s.block_n = pick_block_n(g.n);
-    s.n_terms = n_terms; s.n_planes = n_planes;
+    s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0;
     const int load_n = s.block_n / cg;
     s.a_plane_bytes = kBlockM * kBlockK * 2;
     s.b_plane_bytes = static_cast<uint32_t>(load_n) * kBlockK * 2;
-    s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes);
+    s.a8_plane_bytes = f8 ? kBlockM * kBlockK : 0;
+    s.b8_plane_bytes = f8 ? static_cast<uint32_t>(load_n) * kBlockK : 0;
+    s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes) + 2u * (s.a8_plane_bytes + s.b8_plane_bytes);
     s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack) / static_cast<int>(s.stage_bytes));
     if (s.num_stages < 2) return fail(ZETT_ERR_INVALID, "GEMM tile does not fit two pipeline stages");
     // instruction descriptor (kind::f16): D fp32, A/B bf16|fp16, both K-major, N >> 3, M >> 4
     const uint32_t fmt = split_fmt == kFmtBf16 ? 1u : 0u;
-    s.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(s.block_n >> 3) << 17) |
-              (static_cast<uint32_t>((kBlockM * cg) >> 4) << 24);
-    const CUtensorMap *ta, *tb;
+    const uint32_t shape_bits = (static_cast<uint32_t>(s.block_n >> 3) << 17) | (static_cast<uint32_t>((kBlockM * cg) >> 4) << 24);
+    s.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | shape_bits;
+    s.idesc8 = (1u << 4) | (1u << 7) | (1u << 10) | shape_bits;  // kind::f8f6f4: A, B = E5M2 (1), D = F32
+    const CUtensorMap *ta, *tb, *ta8, *tb8;
     ZETT_TRY(tmap(g.a, g.a_rows, g.k, g.a_plane_stride, kBlockM, n_planes, &ta));
     ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n, n_planes, &tb));
+    ta8 = ta; tb8 = tb;
+    if (f8) {
+      ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, g.a_plane_stride, kBlockM, &ta8));
+      ZETT_TRY(tmap8(g.w_q, g.n, g.k, g.w_plane_stride, load_n, &tb8));
+    }
     const int tile_m = kBlockM * cg;
     const long long m_tiles = (g.m_host + tile_m - 1) / tile_m;
     const long long n_tiles = (g.n + s.block_n - 1) / s.block_n;
@@ -251,8 +301,8 @@ struct GemmEngine {
     attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     ZETT_TRY(time_mark(stream));
-    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, *ta, *tb, s, g.ep));
-    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, *ta, *tb, s, g.ep));
+    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, *ta, *tb, *ta8, *tb8, s, g.ep));
+    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, *ta, *tb, *ta8, *tb8, s, g.ep));
     ZETT_TRY(time_mark(stream));
     return ZETT_OK;
   }
@@ -457,8 +507,8 @@ int take_vector(zett_hn* h, const std::string& name, std::vector<int64_t> shape,
 int split_into(zett_hn* h, const float* src, long long rows, long long k, uint16_t* p0, long long plane_stride) {
   const long long n4 = rows * k / 4;
   const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8));
-  split_planes_kernel<<<std::max(blocks, 1), 256>>>(src, n4, p0, h->gemm.n_terms == 3 ? p0 + plane_stride : nullptr,
-                                                    h->gemm.split_fmt);
+  split_planes_kernel<<<std::max(blocks, 1), 256>>>(src, n4, p0, h->gemm.n_terms != 1 ? p0 + plane_stride : nullptr,
+                                                    h->gemm.split_fmt, true);
   ZETT_CUDA(cudaGetLastError());
   return ZETT_OK;
 }
@@ -497,7 +547,8 @@ int make_projector(zett_hn* h, const std::string& prefix, Projector* p) {
   return ZETT_OK;
 }
 
-uint16_t* plane1(uint16_t* p0, long long stride, const zett_hn* h) { return h->gemm.n_terms == 3 ? p0 + stride : nullptr; }
+// second half of an operand buffer: the lo plane (16-bit split) or the two fp8 planes (kFmtF16F8); none in single-pass mode
+uint16_t* plane1(uint16_t* p0, long long stride, const zett_hn* h) { return h->gemm.n_terms != 1 ? p0 + stride : nullptr; }
 
 int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
   if (max_rows <= 0) return ZETT_OK;
@@ -539,6 +590,8 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   GemmArgs g;
   g.a = a; g.a_rows = cap; g.a_plane_stride = cap * w.k;
   g.w = w.planes + static_cast<long long>(row_off) * w.k; g.w_plane_stride = w.plane_stride();
+  g.a_q = reinterpret_cast<const uint8_t*>(a + g.a_plane_stride);
+  g.w_q = reinterpret_cast<const uint8_t*>(w.planes + w.plane_stride()) + static_cast<long long>(row_off) * w.k;
   g.n = n_rows_w; g.k = w.k;
   if (mclass == kMRows) { g.m_host = m_rows; g.m_dev = nullptr; }
   else { g.m_host = static_cast<int>(cap); g.m_dev = counts + count_slot(mclass); }
@@ -792,7 +845,7 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   if (h->gemm.impl < 1 || h->gemm.impl > 3) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..3"); }
   int terms = cfg->split_terms;
   if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
-  h->gemm.n_terms = (terms == 1) ? 1 : 3;
+  h->gemm.set_precision(terms);
   *out = h;
   return ZETT_OK;
 }
@@ -1009,18 +1062,20 @@ int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev,
   ZETT_TRY(query_device(&eng.dev));
   ZETT_TRY(set_kernel_attrs(&eng.dev));
   eng.impl = impl == 0 ? 2 : impl;
-  eng.n_terms = split_terms == 1 ? 1 : 3;
+  eng.set_precision(split_terms);
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   uint16_t *pa = nullptr, *pw = nullptr;
   ZETT_CUDA(cudaMalloc(&pa, sizeof(uint16_t) * 2 * m * k));
   ZETT_CUDA(cudaMalloc(&pw, sizeof(uint16_t) * 2 * n * k));
   auto cleanup = [&]() { cudaFree(pa); cudaFree(pw); };
-  const int two = eng.n_terms == 3;
-  split_planes_kernel<<<1184, 256, 0, stream>>>(a_dev, m * k / 4, pa, two ? pa + m * k : nullptr, eng.split_fmt);
-  split_planes_kernel<<<1184, 256, 0, stream>>>(w_dev, n * k / 4, pw, two ? pw + n * k : nullptr, eng.split_fmt);
+  const int two = eng.n_terms != 1;
+  split_planes_kernel<<<1184, 256, 0, stream>>>(a_dev, m * k / 4, pa, two ? pa + m * k : nullptr, eng.split_fmt, false);
+  split_planes_kernel<<<1184, 256, 0, stream>>>(w_dev, n * k / 4, pw, two ? pw + n * k : nullptr, eng.split_fmt, true);
   GemmArgs g;
   g.a = pa; g.a_rows = m; g.a_plane_stride = m * k;
   g.w = pw; g.w_plane_stride = n * k;
+  g.a_q = reinterpret_cast<const uint8_t*>(pa + m * k);
+  g.w_q = reinterpret_cast<const uint8_t*>(pw + n * k);
   g.n = static_cast<int>(n); g.k = static_cast<int>(k); g.m_host = static_cast<int>(m);
   g.ep.bias = bias_dev; g.ep.act = act; g.ep.out_f32 = out_dev; g.ep.ld_out = n; g.ep.split_fmt = eng.split_fmt;
   cudaEvent_t e0, e1;

@@ -230,31 +230,23 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const Ga
     phase[buf] ^= 1u;
     const bool rescale = p.scale_w != nullptr && __ldg(p.tok_src + t) >= 0;
     const float* x = stage[buf];
-    uint16_t* o0 = p.out_p0 + static_cast<long long>(t) * p.E;
-    uint16_t* o1 = p.out_p1 ? p.out_p1 + static_cast<long long>(t) * p.E : nullptr;
-    for (int e = tid * 8; e < p.E; e += kGatherThreads * 8) {
+    uint16_t* o0 = p.out_p0;
+    uint16_t* o1 = p.out_p1;
+    for (long long e0 = tid * 8; e0 < p.E; e0 += kGatherThreads * 8) {
+      const long long e = static_cast<long long>(t) * p.E + e0;
       float v[8];
-      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(x + e);
-      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(x + e + 4);
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(x + e0);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(x + e0 + 4);
       if (rescale) {
         float w[8], b[8];
-        *reinterpret_cast<float4*>(w) = __ldg(reinterpret_cast<const float4*>(p.scale_w + e));
-        *reinterpret_cast<float4*>(w + 4) = __ldg(reinterpret_cast<const float4*>(p.scale_w + e + 4));
-        *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(p.scale_b + e));
-        *reinterpret_cast<float4*>(b + 4) = __ldg(reinterpret_cast<const float4*>(p.scale_b + e + 4));
+        *reinterpret_cast<float4*>(w) = __ldg(reinterpret_cast<const float4*>(p.scale_w + e0));
+        *reinterpret_cast<float4*>(w + 4) = __ldg(reinterpret_cast<const float4*>(p.scale_w + e0 + 4));
+        *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(p.scale_b + e0));
+        *reinterpret_cast<float4*>(b + 4) = __ldg(reinterpret_cast<const float4*>(p.scale_b + e0 + 4));
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(__fmul_rn(w[i], v[i]), b[i]);  // Rescaler: w * x + b, two roundings
       }
-      uint16_t a[8], c[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) split16(v[i], p.split_fmt, a[i], c[i]);
-      uint4 pa, pc;
-      pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
-      pa.z = a[4] | (uint32_t(a[5]) << 16); pa.w = a[6] | (uint32_t(a[7]) << 16);
-      pc.x = c[0] | (uint32_t(c[1]) << 16); pc.y = c[2] | (uint32_t(c[3]) << 16);
-      pc.z = c[4] | (uint32_t(c[5]) << 16); pc.w = c[6] | (uint32_t(c[7]) << 16);
-      *reinterpret_cast<uint4*>(o0 + e) = pa;
-      if (o1) *reinterpret_cast<uint4*>(o1 + e) = pc;
+      store_operand8(o0, o1, e, v, p.split_fmt, false);
     }
     __syncthreads();  // everyone is done reading stage[buf] before it is refilled two iterations from now
   }
@@ -316,17 +308,10 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__device__ __forceinline__ void store_split4(uint16_t* p0, uint16_t* p1, long long off, const float4 y, int fmt) {
-  uint16_t a[4], b[4];
-  split16(y.x, fmt, a[0], b[0]);
-  split16(y.y, fmt, a[1], b[1]);
-  split16(y.z, fmt, a[2], b[2]);
-  split16(y.w, fmt, a[3], b[3]);
-  uint2 pa, pb;
-  pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
-  pb.x = b[0] | (uint32_t(b[1]) << 16); pb.y = b[2] | (uint32_t(b[3]) << 16);
-  *reinterpret_cast<uint2*>(p0 + off) = pa;
-  if (p1) *reinterpret_cast<uint2*>(p1 + off) = pb;
+__device__ __forceinline__ void store_split4(uint16_t* p0, uint16_t* p1, long long off, const float4 y, int fmt,
+                                             bool is_weight = false) {
+  const float v[4] = {y.x, y.y, y.z, y.w};
+  store_operand4(p0, p1, off, v, fmt, is_weight);
 }
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
@@ -474,21 +459,17 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
     const float inv = 1.0f / l;
     const long long oi = (p.row0_only ? r : (t0 + i)) * p.ld_out + hoff;
 #pragma unroll
-    for (int d = 0; d < DPL; ++d) {
-      uint16_t a, b;
-      split16(acc[d] * inv, p.split_fmt, a, b);
-      p.out_p0[oi + 32 * d] = a;
-      if (p.out_p1) p.out_p1[oi + 32 * d] = b;
-    }
+    for (int d = 0; d < DPL; ++d) store_operand1(p.out_p0, p.out_p1, oi + 32 * d, acc[d] * inv, p.split_fmt);
   }
 }
 
 // fp32 [rows, cols] -> 16-bit planes (same layout); rows * cols must be a multiple of 4
-__global__ void split_planes_kernel(const float* __restrict__ x, long long n4, uint16_t* p0, uint16_t* p1, int fmt) {
+__global__ void split_planes_kernel(const float* __restrict__ x, long long n4, uint16_t* p0, uint16_t* p1, int fmt,
+                                    bool is_weight) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 y = __ldg(reinterpret_cast<const float4*>(x) + i);
-    store_split4(p0, p1, 4 * i, y, fmt);
+    store_split4(p0, p1, 4 * i, y, fmt, is_weight);
   }
 }
 
@@ -498,55 +479,71 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long n4, u
 // the tensor-core path on the device and selectable (gemm_impl = 3) to bisect a failure; never the default.
 // -------------------------------------------------------------------------------------------------------------------
 struct SimtGemmParams {
-  const uint16_t* a0; const uint16_t* a1;  // [M, K] planes (a1 nullable)
-  const uint16_t* w0; const uint16_t* w1;  // [N, K] planes (w1 nullable)
+  const uint16_t* a0; const uint16_t* a1;  // A planes [M, K] (a1 nullable: single term)
+  const uint16_t* w0; const uint16_t* w1;  // W planes [N, K]
+  const uint8_t* aq; long long aq_stride;  // kFmtF16F8: fp8 planes q0 = aq, q1 = aq + aq_stride
+  const uint8_t* wq; long long wq_stride;
   int m_host; const int* m_dev;
   int n, k;
   int split_fmt;
 };
 
-__device__ __forceinline__ float plane_to_float(uint16_t u, int fmt) {
-  return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
+// value of plane `pl` (0 = main, 1 / 2 = correction planes) of an operand at element offset `off`
+__device__ __forceinline__ float operand_plane(const uint16_t* p0, const uint16_t* p1, const uint8_t* q, long long q_stride,
+                                               long long off, int pl, int fmt) {
+  if (pl == 0) return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(p0[off])) : __half2float(__ushort_as_half(p0[off]));
+  if (fmt == kFmtF16F8) return q ? e5m2_to_float(q[off + (pl == 2 ? q_stride : 0)]) : 0.f;
+  if (!p1) return 0.f;
+  return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(p1[off])) : __half2float(__ushort_as_half(p1[off]));
 }
 
 __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, const EpilogueParams ep) {
-  __shared__ float As0[128][33], As1[128][33], Ws0[32][33], Wsum[32][33];
+  // term t of the product list is As[t] . Ws[t]:  16-bit split: (a0,w0) (a1,w0) (a0,w1);  f16+fp8: (p0,w0) (q0,wq0) (q1,wq1)
+  __shared__ float As[3][128][17], Ws[3][32][17];
   const int M = s.m_dev ? *s.m_dev : s.m_host;
   const int row0 = blockIdx.y * 128, col0 = blockIdx.x * 32;
   if (row0 >= M) return;
   const int tid = threadIdx.x;
+  const bool f8 = s.split_fmt == kFmtF16F8;
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  for (int k0 = 0; k0 < s.k; k0 += 32) {
-    for (int i = tid; i < 128 * 32; i += 128) {
-      const int r = i >> 5, c = i & 31;
+  for (int k0 = 0; k0 < s.k; k0 += 16) {
+    for (int i = tid; i < 128 * 16; i += 128) {
+      const int r = i >> 4, c = i & 15;
       const long long gr = row0 + r;
-      float x0 = 0.f, x1 = 0.f;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (gr < M && k0 + c < s.k) {
-        x0 = plane_to_float(s.a0[gr * s.k + k0 + c], s.split_fmt);
-        if (s.a1) x1 = plane_to_float(s.a1[gr * s.k + k0 + c], s.split_fmt);
+        const long long off = gr * s.k + k0 + c;
+        x0 = operand_plane(s.a0, s.a1, s.aq, s.aq_stride, off, 0, s.split_fmt);
+        x1 = operand_plane(s.a0, s.a1, s.aq, s.aq_stride, off, 1, s.split_fmt);
+        x2 = f8 ? operand_plane(s.a0, s.a1, s.aq, s.aq_stride, off, 2, s.split_fmt) : x0;
       }
-      As0[r][c] = x0;
-      As1[r][c] = x1;
+      As[0][r][c] = x0; As[1][r][c] = x1; As[2][r][c] = x2;
     }
-    for (int i = tid; i < 32 * 32; i += 128) {
-      const int r = i >> 5, c = i & 31;
+    for (int i = tid; i < 32 * 16; i += 128) {
+      const int r = i >> 4, c = i & 15;
       const long long gn = col0 + r;
-      float y0 = 0.f, y1 = 0.f;
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f;
       if (gn < s.n && k0 + c < s.k) {
-        y0 = plane_to_float(s.w0[gn * s.k + k0 + c], s.split_fmt);
-        if (s.w1) y1 = plane_to_float(s.w1[gn * s.k + k0 + c], s.split_fmt);
+        const long long off = gn * s.k + k0 + c;
+        y0 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 0, s.split_fmt);
+        if (f8) {
+          y1 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 1, s.split_fmt);
+          y2 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 2, s.split_fmt);
+        } else {
+          y1 = s.a1 ? y0 : 0.f;
+          y2 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 1, s.split_fmt);
+        }
       }
-      Ws0[r][c] = y0;
-      Wsum[r][c] = y0 + y1;
+      Ws[0][r][c] = y0; Ws[1][r][c] = y1; Ws[2][r][c] = y2;
     }
     __syncthreads();
 #pragma unroll 4
-    for (int kk = 0; kk < 32; ++kk) {
-      const float x0 = As0[tid][kk], x1 = As1[tid][kk];
+    for (int kk = 0; kk < 16; ++kk) {
+      const float x0 = As[0][tid][kk], x1 = As[1][tid][kk], x2 = As[2][tid][kk];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] += x0 * Wsum[c][kk] + x1 * Ws0[c][kk];
+      for (int c = 0; c < 32; ++c) acc[c] += x0 * Ws[0][c][kk] + x1 * Ws[1][c][kk] + x2 * Ws[2][c][kk];
     }
     __syncthreads();
   }

@@ -148,6 +148,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+// D[tmem] (+)= A[smem] * B[smem]; kind::f8f6f4 with e4m3 / e5m2 operands (K = 32 per instruction), fp32 accumulation
+template <int CG>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies fence::before_thread_sync).
 // CG == 2: the arrive is multicast to the same barrier offset in both CTAs of the pair.
 template <int CG>
@@ -179,10 +194,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
-  d |= static_cast<uint64_t>(0) << 16;                            // leading byte offset (unused: one atom along K)
+  d |= static_cast<uint64_t>(1) << 16;                            // leading byte offset (unused for swizzled K-major)
   d |= static_cast<uint64_t>(1024u >> 4) << 32;                   // stride byte offset       bits [32,46)
   d |= static_cast<uint64_t>(1) << 46;                            // descriptor version
   d |= static_cast<uint64_t>(2) << 61;                            // layout type SWIZZLE_128B
+  return d;
+}
+
+// K-major operand tile in smem, 64-byte rows, SWIZZLE_64B (8-row atoms of 512 B): the fp8 correction planes
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;                            // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(512u >> 4) << 32;                    // stride byte offset: 8 rows x 64 B
+  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version
+  d |= static_cast<uint64_t>(4) << 61;                            // layout type SWIZZLE_64B
   return d;
 }
 
