@@ -82,6 +82,37 @@ def run_gemm(impl: int):
     return ok
 
 
+def run_sweep():
+    """Timing probes of the GEMM engine (no parity claim): ms per launch over shapes x terms x rasterisation knobs."""
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    shapes = [(16384, 4096, 4096), (16384, 8192, 4096), (16384, 4096, 8192), (53248, 12288, 4096)]
+    for (m, n, k) in shapes:
+        a = torch.randn(m, k, device=dev)
+        w = torch.randn(n, k, device=dev) / k ** 0.5
+        b = torch.randn(n, device=dev) * 0.1
+        out = torch.empty((m, n), device=dev)
+        for (chunk, group) in ((48, 4), (48, 2), (48, 8), (24, 4), (72, 4), (100000, 16), (100000, 4)):
+            os.environ["ZETT_RASTER_CHUNK_MB"] = str(chunk)
+            os.environ["ZETT_RASTER_GROUP_M"] = str(group)
+            for impl in (2, 1):
+                if impl == 1 and (chunk, group) != (48, 4):
+                    continue
+                for terms in (3, 2, 1):
+                    ms = ctypes.c_float(0)
+                    iters = 4
+                    _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, 0, impl,
+                                                 terms, iters, ctypes.byref(ms), None))
+                    t = ms.value / iters
+                    print(json.dumps(dict(kind="sweep", m=m, n=n, k=k, impl=impl, terms=terms, chunk_mb=chunk, group_m=group,
+                                          ms=round(t, 4), tflops=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1))), flush=True)
+        del a, w, out
+    os.environ.pop("ZETT_RASTER_CHUNK_MB", None)
+    os.environ.pop("ZETT_RASTER_GROUP_M", None)
+    return True
+
+
 def forward_case(name, impl, rows, lang, overrides=None, max_rows_per_pass=0, seed=13, terms=0):
     dev = torch.device("cuda", 0)
     cfg = synthetic.make_config(name, **(overrides or {}))
@@ -149,12 +180,14 @@ FORWARD_CASES = {
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["gemm", "forward"])
+    ap.add_argument("what", choices=["gemm", "forward", "sweep"])
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--configs", default="tiny,tiny_lang,tiny_single_head,tiny_plain,tiny_one_layer,tiny_multi_pass")
     ap.add_argument("--terms", type=int, default=0)
     args = ap.parse_args()
-    if args.what == "gemm":
+    if args.what == "sweep":
+        ok = run_sweep()
+    elif args.what == "gemm":
         ok = run_gemm(args.impl or 2)
     else:
         ok = True

@@ -163,53 +163,88 @@ __device__ __forceinline__ void split16(float x, int fmt, uint16_t& p0, uint16_t
   }
 }
 
-// One thread owns output row `row`, columns [col0, col0 + ncols), ncols <= 32.  col0 is a multiple of 32 and the
-// leading dimensions are multiples of 8, so 16-byte vector stores are aligned whenever a full group is in range.
-__device__ __forceinline__ void epilogue_store32(const EpilogueParams& ep, int row, int col0, int ncols, float* v) {
+// ---------------------------------------------------------------------------------------------------------------
+// One thread owns output row `row`, columns [col0, col0 + 32) (col0 a multiple of 32; leading dimensions multiples of 8,
+// so every vector access below is aligned).  The full-width path keeps the 32 values in registers: every loop is
+// compile-time unrolled and the activation is a template parameter, so nothing is indexed dynamically.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ void epilogue_full32(const EpilogueParams& ep, int row, int col0, float (&v)[32]) {
+  if (ep.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < ncols) {
-      float y = v[j];
-      if (ep.bias) y += __ldg(ep.bias + col0 + j);
-      if (ep.act == kActGeluTanh) y = gelu_tanh_f(y);
-      else if (ep.act == kActGeluErf) y = gelu_erf_f(y);
-      v[j] = y;
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = __ldg(b4 + q);
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
   }
-  if (ep.residual) {
-    const float* r = ep.residual + static_cast<long long>(row) * ep.ld_res + col0;
-    if (ncols == 32) {
+  if (ACT == kActGeluTanh) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(r + j));
-        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-      }
-    } else {
-      for (int j = 0; j < ncols; ++j) v[j] += __ldg(r + j);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+  } else if (ACT == kActGeluErf) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+  }
+  if (ep.residual) {
+    const float4* r4 = reinterpret_cast<const float4*>(ep.residual + static_cast<long long>(row) * ep.ld_res + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(r4 + q);
+      v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
     }
   }
   if (ep.col_scale) {
+    const float4* s4 = reinterpret_cast<const float4*>(ep.col_scale + col0);
+    const float4* t4 = reinterpret_cast<const float4*>(ep.col_shift + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) v[j] = __ldg(ep.col_scale + col0 + j) * v[j] + __ldg(ep.col_shift + col0 + j);
+    for (int q = 0; q < 8; ++q) {
+      const float4 w = __ldg(s4 + q), b = __ldg(t4 + q);
+      // Rescaler: w * y + b with two roundings, as torch evaluates it (modeling_hypernet.py:18-19)
+      v[4 * q] = __fadd_rn(__fmul_rn(w.x, v[4 * q]), b.x);
+      v[4 * q + 1] = __fadd_rn(__fmul_rn(w.y, v[4 * q + 1]), b.y);
+      v[4 * q + 2] = __fadd_rn(__fmul_rn(w.z, v[4 * q + 2]), b.z);
+      v[4 * q + 3] = __fadd_rn(__fmul_rn(w.w, v[4 * q + 3]), b.w);
+    }
   }
   if (ep.out_f32) {
-    float* o = ep.out_f32 + static_cast<long long>(row) * ep.ld_out + col0;
-    if (ncols == 32) {
+    float4* o = reinterpret_cast<float4*>(ep.out_f32 + static_cast<long long>(row) * ep.ld_out + col0);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-      for (int j = 0; j < ncols; ++j) o[j] = v[j];
-    }
+    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
   if (ep.out_p0) {
     const long long off = static_cast<long long>(row) * ep.ld_split + col0;
-    if (ncols == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) store_operand8(ep.out_p0, ep.out_p1, off + j, v + j, ep.split_fmt, false);
-    } else {
-      for (int j = 0; j < ncols; ++j) store_operand1(ep.out_p0, ep.out_p1, off + j, v[j], ep.split_fmt);
+    for (int j = 0; j < 32; j += 8) {
+      const float y[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
+      store_operand8(ep.out_p0, ep.out_p1, off + j, y, ep.split_fmt, false);
     }
+  }
+}
+
+// ragged tail (N not a multiple of 32): element-wise, rarely taken
+__device__ __noinline__ void epilogue_ragged(const EpilogueParams& ep, int row, int col0, int ncols, const float* v) {
+  for (int j = 0; j < ncols; ++j) {
+    float y = v[j];
+    if (ep.bias) y += __ldg(ep.bias + col0 + j);
+    if (ep.act == kActGeluTanh) y = gelu_tanh_f(y);
+    else if (ep.act == kActGeluErf) y = gelu_erf_f(y);
+    if (ep.residual) y += __ldg(ep.residual + static_cast<long long>(row) * ep.ld_res + col0 + j);
+    if (ep.col_scale) y = __fadd_rn(__fmul_rn(__ldg(ep.col_scale + col0 + j), y), __ldg(ep.col_shift + col0 + j));
+    if (ep.out_f32) ep.out_f32[static_cast<long long>(row) * ep.ld_out + col0 + j] = y;
+    if (ep.out_p0) store_operand1(ep.out_p0, ep.out_p1, static_cast<long long>(row) * ep.ld_split + col0 + j, y, ep.split_fmt);
+  }
+}
+
+__device__ __forceinline__ void epilogue_store32(const EpilogueParams& ep, int row, int col0, int ncols, float (&v)[32]) {
+  if (ncols == 32) {
+    if (ep.act == kActGeluTanh) epilogue_full32<kActGeluTanh>(ep, row, col0, v);
+    else if (ep.act == kActGeluErf) epilogue_full32<kActGeluErf>(ep, row, col0, v);
+    else epilogue_full32<kActNone>(ep, row, col0, v);
+  } else {
+    float t[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[j] = v[j];
+    epilogue_ragged(ep, row, col0, ncols, t);
   }
 }
 

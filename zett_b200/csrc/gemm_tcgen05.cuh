@@ -23,7 +23,6 @@ constexpr int kBlockK = 64;         // 64 x 2 B = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 192;   // 6 warps
-constexpr int kGroupM = 16;         // m-tiles per rasterisation group (L2 reuse of the W panel)
 constexpr uint32_t kTmemCols = 512;
 
 struct GemmShape {
@@ -31,6 +30,8 @@ struct GemmShape {
   const int* m_dev;    // optional device-resident row count
   int n, k;
   int block_n;         // 32, 64, 128 or 256
+  int group_m;         // rasterisation: m-tiles per group
+  int chunk_n;         // rasterisation: n-tiles per L2-resident W chunk
   int n_terms;         // 1 or 3
   int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
   int f8;              // 1: operand format kFmtF16F8 -- one fp16 plane + two e5m2 correction planes (epilogue.cuh)
@@ -43,16 +44,25 @@ struct GemmShape {
 
 struct TileCoord { int m_blk, n_blk; };
 
-__device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_tiles) {
-  const int group_tiles = kGroupM * n_tiles;
-  const int g = tile / group_tiles;
-  const int first_m = g * kGroupM;
-  const int gm = min(kGroupM, m_tiles - first_m);
-  const int r = tile - g * group_tiles;
-  TileCoord c;
-  c.m_blk = first_m + r % gm;
-  c.n_blk = r / gm;
-  return c;
+// Rasterisation for L2 residency (the main loop is bound by operand-fetch latency x limited smem buffering, so L2 hits
+// matter more than anything else): N is cut into chunks whose W panel fits comfortably in L2 and stays there while
+// all of M sweeps past it in small m-groups; inside a group m varies fastest, so the CTAs of a wave share W tiles
+// (one DRAM fetch, the rest L2 hits) and each A tile is fetched once per chunk.
+__device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_tiles, int group_m, int chunk_n) {
+  const int chunk_tiles = m_tiles * chunk_n;            // tiles of a full chunk
+  const int c = tile / chunk_tiles;
+  const int first_n = c * chunk_n;
+  const int cn = min(chunk_n, n_tiles - first_n);       // n-tiles of this chunk
+  const int in_chunk = tile - c * chunk_tiles;          // (full chunks precede: their size is m_tiles * chunk_n)
+  const int group_tiles = group_m * cn;
+  const int g = in_chunk / group_tiles;
+  const int first_m = g * group_m;
+  const int gm = min(group_m, m_tiles - first_m);
+  const int r = in_chunk - g * group_tiles;
+  TileCoord t;
+  t.m_blk = first_m + r % gm;
+  t.n_blk = first_n + r / gm;
+  return t;
 }
 
 template <int CG>
@@ -115,7 +125,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const TileCoord tc = tile_coord(tile, m_tiles, n_tiles);
+        const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
         const int row_a = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
         const int row_b = tc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -195,7 +205,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32) are the ones this warp may read
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
-      const TileCoord tc = tile_coord(tile, m_tiles, n_tiles);
+      const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
       mbar_wait(tmem_full_bar(acc), acc_phase, 4);
@@ -203,12 +213,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int row = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
       const int col_tile = tc.n_blk * s.block_n;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
-      for (int c = 0; c < s.block_n; c += 32) {
-        float v[32];
-        tmem_ld_32x32(taddr + static_cast<uint32_t>(c), v);
+      // two register chunks: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed
+      float va[32], vb[32];
+      const bool row_ok = row < M;
+      tmem_ld_32x32(taddr, va);
+      for (int c = 0; c < s.block_n; c += 64) {
         tmem_ld_wait();
-        const int col0 = col_tile + c;
-        if (row < M && col0 < s.n) epilogue_store32(ep, row, col0, min(32, s.n - col0), v);
+        if (c + 32 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), vb);
+        if (row_ok && col_tile + c < s.n) epilogue_store32(ep, row, col_tile + c, min(32, s.n - col_tile - c), va);
+        if (c + 32 < s.block_n) {
+          tmem_ld_wait();
+          if (c + 64 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 64), va);
+          if (row_ok && col_tile + c + 32 < s.n) epilogue_store32(ep, row, col_tile + c + 32, min(32, s.n - col_tile - c - 32), vb);
+        }
       }
       tc_fence_before();
       if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));

@@ -464,12 +464,14 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
 }
 
 // fp32 [rows, cols] -> 16-bit planes (same layout); rows * cols must be a multiple of 4
-__global__ void split_planes_kernel(const float* __restrict__ x, long long n4, uint16_t* p0, uint16_t* p1, int fmt,
-                                    bool is_weight) {
+// `off0`: element offset of x[0] inside the operand buffer (stacked weights), so that the plane addressing of every
+// format is derived from the buffer's base pointers
+__global__ void split_planes_kernel(const float* __restrict__ x, long long n4, uint16_t* p0, uint16_t* p1, long long off0,
+                                    int fmt, bool is_weight) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 y = __ldg(reinterpret_cast<const float4*>(x) + i);
-    store_split4(p0, p1, 4 * i, y, fmt, is_weight);
+    store_split4(p0, p1, off0 + 4 * i, y, fmt, is_weight);
   }
 }
 
