@@ -87,13 +87,13 @@ def run_sweep():
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    shapes = [(16384, 4096, 4096), (16384, 8192, 4096), (16384, 4096, 8192), (53248, 12288, 4096)]
+    shapes = [(16384, 4096, 4096), (16384, 4096, 8192), (53248, 12288, 4096)]
     for (m, n, k) in shapes:
         a = torch.randn(m, k, device=dev)
         w = torch.randn(n, k, device=dev) / k ** 0.5
         b = torch.randn(n, device=dev) * 0.1
         out = torch.empty((m, n), device=dev)
-        for (chunk, group) in ((48, 4), (48, 2), (48, 8), (24, 4), (72, 4), (100000, 16), (100000, 4)):
+        for (chunk, group) in ((48, 4), (100000, 16)):
             os.environ["ZETT_RASTER_CHUNK_MB"] = str(chunk)
             os.environ["ZETT_RASTER_GROUP_M"] = str(group)
             for impl in (2, 1):
@@ -110,6 +110,21 @@ def run_sweep():
         del a, w, out
     os.environ.pop("ZETT_RASTER_CHUNK_MB", None)
     os.environ.pop("ZETT_RASTER_GROUP_M", None)
+    return True
+
+
+def run_one(m, n, k, impl, terms):
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    a = torch.randn(m, k, device=dev)
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    b = torch.randn(n, device=dev) * 0.1
+    out = torch.empty((m, n), device=dev)
+    ms = ctypes.c_float(0)
+    _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, 0, impl, terms, 1,
+                                 ctypes.byref(ms), None))
+    print(json.dumps(dict(kind="one", m=m, n=n, k=k, impl=impl, terms=terms, ms=ms.value)), flush=True)
     return True
 
 
@@ -180,12 +195,16 @@ FORWARD_CASES = {
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["gemm", "forward", "sweep"])
+    ap.add_argument("what", choices=["gemm", "forward", "sweep", "one"])
+    ap.add_argument("--mnk", default="16384,4096,4096")
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--configs", default="tiny,tiny_lang,tiny_single_head,tiny_plain,tiny_one_layer,tiny_multi_pass")
     ap.add_argument("--terms", type=int, default=0)
     args = ap.parse_args()
-    if args.what == "sweep":
+    if args.what == "one":
+        m, n, k = [int(x) for x in args.mnk.split(",")]
+        ok = run_one(m, n, k, args.impl or 2, args.terms or 3)
+    elif args.what == "sweep":
         ok = run_sweep()
     elif args.what == "gemm":
         ok = run_gemm(args.impl or 2)

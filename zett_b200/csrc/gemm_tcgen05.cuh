@@ -19,7 +19,7 @@
 namespace zett {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;         // 64 x 2 B = one 128-byte swizzle row
+constexpr int kMaxBlockK = 64;      // 64 x 2 B = one 128-byte swizzle row; block_k = 32 halves the rows (more, finer stages)
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 192;   // 6 warps
@@ -32,6 +32,8 @@ struct GemmShape {
   int block_n;         // 32, 64, 128 or 256
   int group_m;         // rasterisation: m-tiles per group
   int chunk_n;         // rasterisation: n-tiles per L2-resident W chunk
+  int prefetch_dist;   // k-blocks the L2 prefetch runs ahead of the demand loads (0 = off)
+  int block_k;         // K elements per pipeline stage: 64 (128-byte rows of 16-bit operands) or 32
   int n_terms;         // 1 or 3
   int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
   int f8;              // 1: operand format kFmtF16F8 -- one fp16 plane + two e5m2 correction planes (epilogue.cuh)
@@ -90,7 +92,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int m_tiles = (M + tile_m - 1) / tile_m;
   const int n_tiles = (s.n + s.block_n - 1) / s.block_n;
   const int total_tiles = m_tiles * n_tiles;
-  const int num_kb = (s.k + kBlockK - 1) / kBlockK;
+  const int num_kb = (s.k + s.block_k - 1) / s.block_k;
   const int first_tile = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
   const int load_n = s.block_n / CG;  // rows of the W tile this CTA stages
@@ -103,7 +105,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       prefetch_tmap(&tmap_b8);
     }
     for (int i = 0; i < s.num_stages; ++i) {
-      mbar_init(full_bar(i), CG);   // one arrive(+tx) per producing CTA, all on the leader's barrier
+      mbar_init(full_bar(i), 1);    // the leader's arrive.expect_tx covers the bytes of every CTA of the group
       mbar_init(empty_bar(i), 1);   // one tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
@@ -124,11 +126,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 prefetch cursor: walks the same (tile, k-block) sequence `prefetch_dist` steps ahead of the demand loads.
+      // The main loop is bound by fetch latency x the ~190 KB of smem that can be in flight; a DRAM miss in any line
+      // of a stage delays the whole stage, so the misses are taken early, by requests that need no smem.
+      int pf_tile = first_tile, pf_kb = 0, pf_row_a = 0, pf_row_b = 0;
+      auto pf_rows = [&]() {
+        if (pf_tile < total_tiles) {
+          const TileCoord pc = tile_coord(pf_tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
+          pf_row_a = pc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
+          pf_row_b = pc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
+        }
+      };
+      auto pf_step = [&]() {
+        if (pf_tile >= total_tiles) return;
+        tma_prefetch_3d(&tmap_a, pf_kb * s.block_k, pf_row_a, 0);
+        tma_prefetch_3d(&tmap_b, pf_kb * s.block_k, pf_row_b, 0);
+        if (s.f8) {
+          tma_prefetch_3d(&tmap_a8, pf_kb * s.block_k, pf_row_a, 0);
+          tma_prefetch_3d(&tmap_b8, pf_kb * s.block_k, pf_row_b, 0);
+        }
+        if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += tile_step; pf_rows(); }
+      };
+      pf_rows();
+      for (int i = 0; i < s.prefetch_dist; ++i) pf_step();
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
         const int row_a = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
         const int row_b = tc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (s.prefetch_dist > 0) pf_step();
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
           const uint32_t a_dst = smem_base + stage * s.stage_bytes;
           const uint32_t b_dst = a_dst + s.n_planes * s.a_plane_bytes;
@@ -136,20 +162,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t b8_dst = a8_dst + 2u * s.a8_plane_bytes;
           if constexpr (CG == 1) {
             mbar_expect_tx(full_bar(stage), s.stage_bytes);
-            tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * kBlockK, row_a, 0);
-            tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * kBlockK, row_b, 0);
+            tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0);
+            tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0);
             if (s.f8) {
-              tma_load_3d(&tmap_a8, full_bar(stage), a8_dst, kb * kBlockK, row_a, 0);
-              tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * kBlockK, row_b, 0);
+              tma_load_3d(&tmap_a8, full_bar(stage), a8_dst, kb * s.block_k, row_a, 0);
+              tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
             }
           } else {
+            // only the leader arrives (expecting both CTAs' bytes); the peer's copies credit the leader's barrier
+            // directly, so the peer's loop carries no cluster-scope operation.  Its bytes may land before the
+            // leader's expect_tx: the phase cannot complete until that arrive, and the transaction count is signed.
             if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
-            else mbar_arrive_cluster(full_bar(stage), 0);
-            tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * kBlockK, row_a, 0);
-            tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * kBlockK, row_b, 0);
+            tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0);
+            tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0);
             if (s.f8) {
-              tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * kBlockK, row_a, 0);
-              tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * kBlockK, row_b, 0);
+              tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * s.block_k, row_a, 0);
+              tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
             }
           }
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
@@ -173,10 +201,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tc_fence_after();
           const uint32_t a0 = smem_base + stage * s.stage_bytes;
           const uint32_t b0 = a0 + s.n_planes * s.a_plane_bytes;
-          const uint64_t da0 = umma_desc_sw128(a0), db0 = umma_desc_sw128(b0);
-          const uint64_t da1 = umma_desc_sw128(a0 + s.a_plane_bytes), db1 = umma_desc_sw128(b0 + s.b_plane_bytes);
-#pragma unroll
-          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+          const uint32_t row16 = static_cast<uint32_t>(s.block_k) * 2u;  // bytes per row of a 16-bit plane
+          const uint64_t da0 = umma_desc_kmajor(a0, row16), db0 = umma_desc_kmajor(b0, row16);
+          const uint64_t da1 = umma_desc_kmajor(a0 + s.a_plane_bytes, row16), db1 = umma_desc_kmajor(b0 + s.b_plane_bytes, row16);
+          const int ksteps = s.block_k / kUmmaK;
+#pragma unroll 4
+          for (int kk = 0; kk < ksteps; ++kk) {
             const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
             umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
             if (s.n_terms == 3 && !s.f8) {
@@ -189,9 +219,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t b8 = a8 + 2u * s.a8_plane_bytes;
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
-              const uint64_t dqa = umma_desc_sw64(a8 + pl * s.a8_plane_bytes), dqb = umma_desc_sw64(b8 + pl * s.b8_plane_bytes);
-#pragma unroll
-              for (int kk = 0; kk < kBlockK / 32; ++kk) umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, 1u);
+              const uint64_t dqa = umma_desc_kmajor(a8 + pl * s.a8_plane_bytes, static_cast<uint32_t>(s.block_k));
+              const uint64_t dqb = umma_desc_kmajor(b8 + pl * s.b8_plane_bytes, static_cast<uint32_t>(s.block_k));
+              for (int kk = 0; kk < s.block_k / 32; ++kk) umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, 1u);
             }
           }
           umma_commit<CG>(empty_bar(stage));                       // frees the smem stage (both CTAs)

@@ -66,18 +66,22 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 // 3-D map {K, rows, planes} over 16-bit planes, box {64, box_rows, n_planes}, 128-byte swizzle, zero fill out of bounds
+CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long long k, long long plane_stride_elems,
-                    int box_rows, int n_planes, int split_fmt) {
+                    int box_rows, int n_planes, int split_fmt, int block_k) {
   EncodeTiledFn enc;
   ZETT_TRY(get_encode_fn(&enc));
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(n_planes)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(k) * 2u, static_cast<cuuint64_t>(plane_stride_elems) * 2u};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(n_planes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(n_planes)};
   cuuint32_t estr[3] = {1, 1, 1};
   if (n_planes == 1) strides[1] = strides[0] * static_cast<cuuint64_t>(rows);
   const CUtensorMapDataType dt = split_fmt == kFmtBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(map, dt, 3, const_cast<uint16_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle_for_row_bytes(block_k * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%lld k=%lld plane_stride=%lld box_rows=%d planes=%d",
@@ -89,15 +93,15 @@ int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long
 
 // 3-D map {K, rows, 2} over the two e5m2 correction planes, box {64, box_rows, 2}, 64-byte swizzle
 int make_plane8_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long k, long long plane_stride_bytes,
-                     int box_rows) {
+                     int box_rows, int block_k) {
   EncodeTiledFn enc;
   ZETT_TRY(get_encode_fn(&enc));
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), 2};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(plane_stride_bytes)};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), 2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -179,6 +183,8 @@ struct GemmEngine {
   void read_env() {
     if (const char* e = getenv("ZETT_RASTER_CHUNK_MB")) raster_chunk_bytes = std::max(1ll, atoll(e)) << 20;
     if (const char* e = getenv("ZETT_RASTER_GROUP_M")) raster_group_m = std::max(1, atoi(e));
+    if (const char* e = getenv("ZETT_PREFETCH_DIST")) prefetch_dist = std::max(0, atoi(e));
+    if (const char* e = getenv("ZETT_BLOCK_K")) block_k = atoi(e) == 32 ? 32 : 64;
   }
   void set_precision(int terms) {
     n_terms = (terms == 1 || terms == 2) ? terms : 3;
@@ -188,6 +194,8 @@ struct GemmEngine {
   // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
   long long raster_chunk_bytes = 48ll << 20;
   int raster_group_m = 4;
+  int prefetch_dist = 0;   // L2 prefetch ahead of the demand loads: measured to hurt (doubles DRAM reads), kept as a knob
+  int block_k = 64;        // K per pipeline stage (64 or 32)
   bool timing = false;
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
@@ -216,22 +224,22 @@ struct GemmEngine {
 
   int tmap(const uint16_t* base, long long rows, long long k, long long plane_stride, int box_rows, int n_planes,
            const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows, n_planes);
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k, n_planes);
     auto it = tmaps.find(key);
     if (it == tmaps.end()) {
       CUtensorMap m;
-      ZETT_TRY(make_plane_tmap(&m, base, rows, k, plane_stride, box_rows, n_planes, split_fmt));
+      ZETT_TRY(make_plane_tmap(&m, base, rows, k, plane_stride, box_rows, n_planes, split_fmt, block_k));
       it = tmaps.emplace(key, m).first;
     }
     *out = &it->second;
     return ZETT_OK;
   }
   int tmap8(const uint8_t* base, long long rows, long long k, long long plane_stride, int box_rows, const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows, 8);
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k, 8);
     auto it = tmaps.find(key);
     if (it == tmaps.end()) {
       CUtensorMap m;
-      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, plane_stride, box_rows));
+      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, plane_stride, box_rows, block_k));
       it = tmaps.emplace(key, m).first;
     }
     *out = &it->second;
@@ -270,10 +278,11 @@ struct GemmEngine {
     s.block_n = pick_block_n(g.n);
     s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0;
     const int load_n = s.block_n / cg;
-    s.a_plane_bytes = kBlockM * kBlockK * 2;
-    s.b_plane_bytes = static_cast<uint32_t>(load_n) * kBlockK * 2;
-    s.a8_plane_bytes = f8 ? kBlockM * kBlockK : 0;
-    s.b8_plane_bytes = f8 ? static_cast<uint32_t>(load_n) * kBlockK : 0;
+    s.block_k = block_k;
+    s.a_plane_bytes = kBlockM * block_k * 2;
+    s.b_plane_bytes = static_cast<uint32_t>(load_n) * block_k * 2;
+    s.a8_plane_bytes = f8 ? kBlockM * block_k : 0;
+    s.b8_plane_bytes = f8 ? static_cast<uint32_t>(load_n) * block_k : 0;
     s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes) + 2u * (s.a8_plane_bytes + s.b8_plane_bytes);
     s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack) / static_cast<int>(s.stage_bytes));
     if (s.num_stages < 2) return fail(ZETT_ERR_INVALID, "GEMM tile does not fit two pipeline stages");
@@ -297,6 +306,7 @@ struct GemmEngine {
     const long long w_tile_bytes = static_cast<long long>(s.block_n) * g.k * (n_terms == 1 ? 2 : 4);
     s.chunk_n = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, raster_chunk_bytes / std::max<long long>(w_tile_bytes, 1))));
     s.group_m = raster_group_m;
+    s.prefetch_dist = prefetch_dist;
     const long long tiles = m_tiles * n_tiles;
     if (tiles == 0) return ZETT_OK;
     int ctas = static_cast<int>(std::min<long long>(dev.num_sms / cg, tiles)) * cg;
@@ -642,7 +652,8 @@ int count_slot(MClass m) { return m == kMSurface ? kCntSurface : (m == kMEncoder
 // One Linear layer through the GEMM engine.  `a` / `out_*` are plane-0 pointers; `cap` = rows the buffers hold.
 int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const uint16_t* a, long long cap, MClass mclass,
                int m_rows, const int* counts, int act, float* out_f32, long long ld_f32, uint16_t* out_p0,
-               long long out_cap, const float* col_scale, const float* col_shift, cudaStream_t stream) {
+               long long out_cap, const float* col_scale, const float* col_shift, cudaStream_t stream,
+               const float* residual = nullptr) {
   GemmArgs g;
   g.a = a; g.a_rows = cap; g.a_plane_stride = cap * w.k;
   g.w = w.planes + static_cast<long long>(row_off) * w.k; g.w_plane_stride = w.plane_stride();
@@ -654,6 +665,7 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   g.ep.bias = w.bias + row_off;
   g.ep.act = act;
   g.ep.col_scale = col_scale; g.ep.col_shift = col_shift;
+  g.ep.residual = residual; g.ep.ld_res = n_rows_w;  // residual stream rows are [*, n]; added after the activation
   g.ep.out_f32 = out_f32; g.ep.ld_out = ld_f32;
   g.ep.out_p0 = out_p0; g.ep.out_p1 = out_p0 ? plane1(out_p0, out_cap * n_rows_w, h) : nullptr; g.ep.ld_split = n_rows_w;
   g.ep.split_fmt = h->gemm.split_fmt;
@@ -676,8 +688,8 @@ int run_projector(zett_hn* h, const Projector& pb, const uint16_t* xp, const flo
   ZETT_TRY(run_linear(h, pb.dense1, 0, h->I, xp, cap, mclass, m_rows, counts, kActGeluTanh, nullptr, 0, pg, cap, nullptr,
                       nullptr, stream));
   ZETT_TRY(run_linear(h, pb.dense2, 0, h->H, pg, cap, mclass, m_rows, counts, kActGeluTanh, z, h->H, nullptr, 0, nullptr,
-                      nullptr, stream));
-  ln_out.a = z; ln_out.lda = h->H; ln_out.res = xf;
+                      nullptr, stream, xf));  // z = gelu(dense2(.)) + x, the residual rides in the GEMM epilogue
+  ln_out.a = z; ln_out.lda = h->H; ln_out.res = nullptr;
   ln_out.gamma = pb.ln_w; ln_out.beta = pb.ln_b; ln_out.eps = 1e-6f;
   if (mclass == kMRows) { ln_out.n_dev = nullptr; ln_out.n_host = m_rows; }
   else { ln_out.n_dev = counts + count_slot(mclass); ln_out.n_host = 0; }
@@ -773,17 +785,17 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
       ap.split_fmt = fmt;
       ZETT_TRY(launch_attention(h, ap, stream));
       ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.PH_b, cap2, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, 0, nullptr,
-                          nullptr, stream));
+                          nullptr, stream, w.F3));
       LnParams l1{};
-      l1.a = w.F2; l1.lda = H; l1.res = w.F3; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
+      l1.a = w.F2; l1.lda = H; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
       l1.n_dev = counts + kCntEncoder; l1.out_f32 = w.F1; l1.out_p0 = w.PH_b; l1.out_p1 = plane1(w.PH_b, cap2 * H, h);
       ZETT_TRY(launch_ln(h, l1, cap2, stream));
       ZETT_TRY(run_linear(h, ly.inter, 0, I, w.PH_b, cap2, kMEncoder, 0, counts, kActGeluErf, nullptr, 0, w.PI, cap2, nullptr,
                           nullptr, stream));
       ZETT_TRY(run_linear(h, ly.out, 0, H, w.PI, cap2, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, 0, nullptr, nullptr,
-                          stream));
+                          stream, w.F1));
       LnParams l2{};
-      l2.a = w.F2; l2.lda = H; l2.res = w.F1; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
+      l2.a = w.F2; l2.lda = H; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
       l2.n_dev = counts + kCntEncoder; l2.out_f32 = w.F3; l2.out_p0 = w.PH_a; l2.out_p1 = plane1(w.PH_a, cap2 * H, h);
       if (l == n_layers - 2) {  // the pruned last layer reads position 0 of every row from compact buffers
         l2.tok_row = w.tok2_row; l2.row_start = w.row_start2;
@@ -803,17 +815,17 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
       ap.split_fmt = fmt;
       ZETT_TRY(launch_attention(h, ap, stream));
       ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.CPC, capr, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, 0, nullptr,
-                          nullptr, stream));
+                          nullptr, stream, w.CX0));
       LnParams l1{};
-      l1.a = w.CZ; l1.lda = H; l1.res = w.CX0; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
+      l1.a = w.CZ; l1.lda = H; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
       l1.n_host = rows; l1.out_f32 = w.CX1; l1.out_p0 = w.CPX1; l1.out_p1 = plane1(w.CPX1, capr * H, h);
       ZETT_TRY(launch_ln(h, l1, rows, stream));
       ZETT_TRY(run_linear(h, ly.inter, 0, I, w.CPX1, capr, kMRows, rows, counts, kActGeluErf, nullptr, 0, w.CPG, capr, nullptr,
                           nullptr, stream));
       ZETT_TRY(run_linear(h, ly.out, 0, H, w.CPG, capr, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, 0, nullptr, nullptr,
-                          stream));
+                          stream, w.CX1));
       LnParams l2{};
-      l2.a = w.CZ; l2.lda = H; l2.res = w.CX1; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
+      l2.a = w.CZ; l2.lda = H; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
       l2.n_host = rows; l2.out_f32 = w.CH0; l2.out_p0 = w.CPH0; l2.out_p1 = plane1(w.CPH0, capr * H, h);
       if (h->cfg.hn_predict_bias) {  // bias_projection(hidden[:, 0])[..., 0]  (:260-261)
         l2.dot_w = h->biasproj_w; l2.dot_b = h->biasproj_b; l2.dot_out = pred_bias; l2.dot_ld = ld_bias;

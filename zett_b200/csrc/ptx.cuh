@@ -104,6 +104,11 @@ __device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t bar, 
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// prefetch one box of a tiled tensor into L2 (no smem, no barrier): turns the later demand load into an L2 hit
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // 1-D bulk copy global -> smem (gather of whole embedding rows)
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -192,25 +197,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile in smem, 128-byte rows, SWIZZLE_128B (8-row atoms of 1024 B), sm_100 descriptor version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptor (sm_100, version 1) of a K-major operand tile whose rows are `row_bytes` long and
+// swizzled with the matching TMA mode: 128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B, 32 B -> SWIZZLE_32B.  Rows are
+// grouped in 8-row atoms (stride byte offset = 8 * row_bytes); the leading byte offset is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                            // leading byte offset (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;                   // stride byte offset       bits [32,46)
+  d |= static_cast<uint64_t>(1) << 16;                            // leading byte offset      bits [16,30)
+  d |= static_cast<uint64_t>((8u * row_bytes) >> 4) << 32;        // stride byte offset       bits [32,46)
   d |= static_cast<uint64_t>(1) << 46;                            // descriptor version
-  d |= static_cast<uint64_t>(2) << 61;                            // layout type SWIZZLE_128B
-  return d;
-}
-
-// K-major operand tile in smem, 64-byte rows, SWIZZLE_64B (8-row atoms of 512 B): the fp8 correction planes
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;                            // leading byte offset (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(512u >> 4) << 32;                    // stride byte offset: 8 rows x 64 B
-  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version
-  d |= static_cast<uint64_t>(4) << 61;                            // layout type SWIZZLE_64B
+  d |= layout << 61;                                              // swizzle mode
   return d;
 }
 
