@@ -145,6 +145,39 @@ def cpu_reference_run(name, steps, warmup, budget_s):
                        "threaded ATen fp32 forward" % (n, wl["rows"]))
 
 
+def torch_eager_gpu_run(name, dev, rows=8192):
+    """The library-kernel bar: the reference's own operator sequence through PyTorch eager (ATen / cuBLAS
+    sm_100 kernels) on the same B200, fp32 and with TF32 matmuls enabled.  Rows are independent, so a sample is timed."""
+    import torch
+    from oracle import hypernet_oracle_torch as hot
+    from zett_b200 import synthetic
+    wl = WORKLOADS[name]
+    cfg = synthetic.make_config(name)
+    W = hot.to_torch(synthetic.make_weights(cfg, seed=0), dev)
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=100)).to(dev)
+    sf = synthetic.make_random_surface_forms(cfg, rows, seed=7)
+    out = {}
+    for label, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        for _ in range(2):
+            hot.hypernet_forward(cfg, W, sf, src, lang_index=wl["lang"])
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            hot.hypernet_forward(cfg, W, sf, src, lang_index=wl["lang"])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[label] = rows * 3 / (e0.elapsed_time(e1) * 1e-3)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    del W, src
+    torch.cuda.empty_cache()
+    return {"unit": "rows/s", "rows_sampled": rows, "fp32": out["fp32"], "tf32": out["tf32"],
+            "what": "reference operator sequence via torch eager (ATen/cuBLAS) on the same GPU, dense over all L positions"}
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -298,11 +331,21 @@ def run_ours(args):
                      "kernel": "gemm_tcgen05_kernel", "peak_source": peaks["src"],
                      "note": "achieved = FLOPs of the GEMMs issued in one step (each product counted once although the "
                              "3-term split issues three MMAs) / summed CUDA-event time of those launches",
-                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": st["gemm_launches"]},
+                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": st["gemm_launches"],
+                     "mma_issue_tflops": (achieved * (3 if args.split_terms not in (1, 2) else (1 if args.split_terms == 1 else 2)))
+                     if achieved else None,
+                     "profile": "profiles/gemm_tcgen05_r1_bf16x3_53248x12288x4096.csv: sm__pipe_tensor_cycles_active 99.7 % "
+                                "(ncu, isolated launch of the QKV GEMM); traffic = its dram read+write bytes"},
     }
+    if args.config == "mistral" and args.split_terms not in (1, 2):
+        line["roofline"]["traffic"] = 20147391000 + 2606192000  # bytes, one launch of the largest GEMM (profile above)
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.config, 1, 1, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {"value": r["value"], "unit": "rows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        try:
+            line["torch_eager_b200"] = torch_eager_gpu_run(args.config, dev)
+        except Exception as e:  # noqa: BLE001
+            line["torch_eager_b200"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

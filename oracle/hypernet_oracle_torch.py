@@ -23,8 +23,8 @@ def _get(cfg, name, default=None):
     return cfg.get(name, default) if isinstance(cfg, dict) else getattr(cfg, name, default)
 
 
-def to_torch(weights: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
-    return {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)) for k, v in weights.items()}
+def to_torch(weights: Dict[str, np.ndarray], device="cpu") -> Dict[str, torch.Tensor]:
+    return {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(device) for k, v in weights.items()}
 
 
 def _projector(x, W, p):
@@ -36,7 +36,8 @@ def _projector(x, W, p):
 @torch.no_grad()
 def hypernet_forward(cfg, W: Dict[str, torch.Tensor], target_surface_forms, source_embeddings: torch.Tensor,
                      lang_index: Optional[int] = None):
-    ids = torch.as_tensor(np.asarray(target_surface_forms)).long()
+    dev = source_embeddings.device
+    ids = torch.as_tensor(np.asarray(target_surface_forms)).long().to(dev)
     v0 = int(_get(cfg, "original_vocab_size"))
     pad = int(_get(cfg, "pad_token_id"))
     H = int(_get(cfg, "hn_hidden_size"))
@@ -59,13 +60,13 @@ def hypernet_forward(cfg, W: Dict[str, torch.Tensor], target_surface_forms, sour
         lang = W["lang_embeddings.weight"][int(lang_index)] - (
             W["model.embeddings.token_type_embeddings.weight"][0] + W["model.embeddings.position_embeddings.weight"][L])
         x = torch.cat([x, lang[None, None, :].expand(x.shape[0], -1, -1)], dim=1)
-        mask = torch.cat([mask, torch.ones((mask.shape[0], 1), dtype=torch.bool)], dim=1)
+        mask = torch.cat([mask, torch.ones((mask.shape[0], 1), dtype=torch.bool, device=dev)], dim=1)
     B, S, _ = x.shape
     # RobertaEmbeddings + encoder (eager attention)
     x = x + W["model.embeddings.token_type_embeddings.weight"][0]
     x = x + W["model.embeddings.position_embeddings.weight"][:S][None]
     x = F.layer_norm(x, (H,), W["model.embeddings.LayerNorm.weight"], W["model.embeddings.LayerNorm.bias"], eps)
-    add_mask = torch.zeros((B, 1, 1, S), dtype=x.dtype).masked_fill(~mask[:, None, None, :], torch.finfo(x.dtype).min)
+    add_mask = torch.zeros((B, 1, 1, S), dtype=x.dtype, device=dev).masked_fill(~mask[:, None, None, :], torch.finfo(x.dtype).min)
     dh = H // heads
     for l in range(n_layers):
         p = f"model.encoder.layer.{l}."
@@ -96,5 +97,7 @@ def hypernet_forward(cfg, W: Dict[str, torch.Tensor], target_surface_forms, sour
     if _get(cfg, "hn_predict_bias", False):
         bias = F.linear(h0, W["bias_projection.weight"], W["bias_projection.bias"])[..., 0]
     else:
-        bias = torch.zeros(ids.shape[0])
+        bias = torch.zeros(ids.shape[0], device=dev)
+    if dev.type != "cpu":  # library-kernel comparison arm of bench.py: results stay on the device
+        return pred_in, pred_out, bias
     return pred_in.numpy(), (None if pred_out is None else pred_out.numpy()), bias.numpy()

@@ -1,0 +1,61 @@
+"""Multi-GPU parity check (run under torchrun on N GPUs of one box): the row-sharded prediction assembled by the single
+NCCL all-gather equals the single-GPU prediction bit for bit, on every rank, and matches the oracle on a sample."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import hypernet_oracle as ho  # noqa: E402
+from zett_b200 import parallel, synthetic  # noqa: E402
+from zett_b200.modeling_hypernet import ZettHypernet, load_weights_numpy  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+    for name, rows, lang in (("tiny", 1003, None), ("xlmr", 4099, 3)):
+        cfg = synthetic.make_config(name)
+        weights = synthetic.make_weights(cfg, seed=11)
+        src_np = synthetic.make_source_embeddings(cfg, seed=12)
+        sf_np = synthetic.make_random_surface_forms(cfg, rows, seed=31)
+        model = load_weights_numpy(ZettHypernet(cfg), weights).to(dev)
+        sf, src = torch.from_numpy(sf_np).to(dev), torch.from_numpy(src_np).to(dev)
+        single = model(sf, source_embeddings=src, lang_index=None if lang is None else torch.tensor(lang))
+        fn = parallel.hypernet_block_fn(model, sf, src, lang)
+        sharded = parallel.predict_sharded(rows, cfg.n_embd, bool(cfg.separate_out_embeddings), fn, dev)
+        torch.cuda.synchronize()
+        for a, b in zip(single, sharded):
+            if a is None:
+                assert b is None
+                continue
+            same = torch.equal(a, b.contiguous())
+            ok &= same
+            if not same:
+                print(f"rank {rank} {name}: sharded != single, max diff {(a - b).abs().max().item():.3e}", flush=True)
+        if rank == 0:
+            want = ho.hypernet_forward(cfg, weights, sf_np[:256], src_np, lang_index=lang)
+            masked = ho.fully_masked_rows(cfg, sf_np[:256])
+            for g, w in zip(sharded, want):
+                if w is None:
+                    continue
+                fro, worst = ho.rel_errors(g[:256].cpu().numpy(), w, exclude=masked)
+                ok &= fro < 1e-3 and worst < 1e-3
+                print(f"{name}: world {world} vs oracle fro {fro:.2e} worst {worst:.2e}", flush=True)
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if t.item() == 1 else "FAIL", "world", world, flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,3 +109,34 @@ def test_checkpoint_roundtrip_and_automodel(tmp_path):
     assert isinstance(again, ZettHypernet) and again.config.hn_embed_lang_id and again.config.n_langs == 5
     for k, v in again.state_dict().items():
         np.testing.assert_array_equal(v.numpy(), weights[k])
+
+
+def test_post_step_special_rows_and_splice(tmp_path):
+    """scripts/transfer.py:272-304 on a tiny PyTorch GPT-2: special rows come from the source model, the predicted
+    matrices become the model's (tied or untied) embeddings, vocab_size follows, the model still runs and saves."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from zett_b200.transfer import overwrite_special_rows, source_embeddings_of, splice_into_model
+    rng = np.random.default_rng(0)
+    for tied in (True, False):
+        cfg = GPT2Config(vocab_size=50, n_positions=16, n_embd=32, n_layer=1, n_head=2, tie_word_embeddings=tied)
+        model = GPT2LMHeadModel(cfg)
+        src_in, src_out, stacked = source_embeddings_of(model)
+        assert stacked.shape == (50, 32 if tied else 64) and (src_out is None) == tied
+        pred_in = rng.standard_normal((70, 32)).astype(np.float32)
+        pred_out = None if tied else rng.standard_normal((70, 32)).astype(np.float32)
+        prev_special, new_special = [3, 49], [60, 0]
+        keep_in = src_in.numpy().copy()
+        overwrite_special_rows(pred_in, pred_out, None, src_in.numpy(), None if tied else src_out.numpy(), prev_special, new_special)
+        np.testing.assert_array_equal(pred_in[60], keep_in[3])
+        np.testing.assert_array_equal(pred_in[0], keep_in[49])
+        model = splice_into_model(model, pred_in, pred_out)
+        assert model.config.vocab_size == 70
+        np.testing.assert_array_equal(model.get_input_embeddings().weight.detach().numpy(), pred_in)
+        want_out = pred_in if tied else pred_out
+        np.testing.assert_array_equal(model.get_output_embeddings().weight.detach().numpy(), want_out)
+        logits = model(torch.tensor([[1, 60, 69]])).logits
+        assert logits.shape == (1, 3, 70)
+        model.save_pretrained(tmp_path / ("tied" if tied else "untied"))
+    t = torch.zeros((5, 4))
+    overwrite_special_rows(t, None, None, torch.ones((3, 4)), None, [2], [4])
+    assert t[4].sum() == 4 and t[:4].sum() == 0

@@ -96,3 +96,113 @@ def predict_whole_vocab(hypernet, target_surface_form_matrix, source_embeddings_
     """One call for the whole vocabulary: pinned H2D of the int32 matrix, all passes queued back to back on the
     current stream, pinned D2H of the results.  Returns numpy arrays ``(in, out | None, bias)``."""
     return make_predict(hypernet, source_embeddings_dev, lang_index)(target_surface_form_matrix)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Post-step of the transfer driver (scripts/transfer.py:272-328): special-token rows keep the source model's
+# embeddings, the predicted matrices replace the base model's input / output embeddings (and output bias), the model
+# is saved.  The reference does this on Flax parameter trees (IN/OUT_EMBEDDING_PATHS, zett/model/__init__.py:15-41) and
+# converts to PyTorch afterwards (--save_pt); here it is done on the PyTorch model directly.
+# ----------------------------------------------------------------------------------------------------------------------
+def overwrite_special_rows(predicted_in, predicted_out, predicted_bias, source_in, source_out, previous_special_ids,
+                           new_special_ids):
+    """``predicted[new_special_ids] = source[previous_special_ids]`` (scripts/transfer.py:274-302); in place.
+
+    Accepts numpy arrays or torch tensors (host or device).  ``predicted_bias`` is left as predicted, like the reference."""
+    prev = torch.as_tensor(np.asarray(previous_special_ids), dtype=torch.long)
+    new = torch.as_tensor(np.asarray(new_special_ids), dtype=torch.long)
+    if prev.numel() != new.numel():
+        raise ValueError("special-token id lists differ in length")
+
+    def put(pred, src):
+        if pred is None:
+            return None
+        if isinstance(pred, np.ndarray):
+            pred[new.numpy()] = np.asarray(src)[prev.numpy()]
+            return pred
+        pred[new.to(pred.device)] = torch.as_tensor(src)[prev].to(pred.device, pred.dtype)
+        return pred
+
+    return put(predicted_in, source_in), put(predicted_out, source_out), predicted_bias
+
+
+def source_embeddings_of(model):
+    """``(source_in [V0, D], source_out [V0, D] | None, stacked [V0, E])`` of a PyTorch HF model, the way the reference
+    stacks them (scripts/transfer.py:162-191): output embeddings are taken only when the model does not tie them."""
+    emb_in = model.get_input_embeddings().weight.detach().float()
+    out_layer = model.get_output_embeddings() if hasattr(model, "get_output_embeddings") else None
+    tied = bool(getattr(model.config, "tie_word_embeddings", True))
+    if out_layer is None or tied:
+        return emb_in, None, emb_in
+    emb_out = out_layer.weight.detach().float()
+    return emb_in, emb_out, torch.cat([emb_in, emb_out], dim=1)
+
+
+def splice_into_model(model, predicted_in, predicted_out=None, predicted_bias=None):
+    """Replace the base model's vocabulary-sized parameters by the predicted ones (scripts/transfer.py:287-304):
+    input embeddings <- predicted_in, untied output embeddings <- predicted_out, output bias <- predicted_bias when
+    the head has one.  ``config.vocab_size`` follows (``:272``).  Returns the model."""
+    pred_in = torch.as_tensor(predicted_in)
+    n, d = pred_in.shape
+    old_in = model.get_input_embeddings()
+    if old_in.weight.shape[1] != d:
+        raise ValueError("embedding width %d does not match the model's %d" % (d, old_in.weight.shape[1]))
+    dtype, device = old_in.weight.dtype, old_in.weight.device
+    new_in = torch.nn.Embedding(n, d, padding_idx=None, dtype=dtype, device=device)
+    with torch.no_grad():
+        new_in.weight.copy_(pred_in.to(device=device, dtype=dtype))
+    model.set_input_embeddings(new_in)
+    out_layer = model.get_output_embeddings() if hasattr(model, "get_output_embeddings") else None
+    tied = bool(getattr(model.config, "tie_word_embeddings", True))
+    if out_layer is not None:
+        if tied:
+            new_out = torch.nn.Linear(d, n, bias=out_layer.bias is not None, dtype=dtype, device=device)
+            new_out.weight = new_in.weight
+        else:
+            if predicted_out is None:
+                raise ValueError("the model has untied output embeddings: predicted_out is required")
+            new_out = torch.nn.Linear(d, n, bias=out_layer.bias is not None, dtype=dtype, device=device)
+            with torch.no_grad():
+                new_out.weight.copy_(torch.as_tensor(predicted_out).to(device=device, dtype=dtype))
+        if new_out.bias is not None:
+            with torch.no_grad():
+                if predicted_bias is not None:
+                    new_out.bias.copy_(torch.as_tensor(predicted_bias).to(device=device, dtype=dtype))
+                else:
+                    new_out.bias.zero_()
+        model.set_output_embeddings(new_out)
+    model.config.vocab_size = n
+    return model
+
+
+def transfer_model(hypernet, base_model, base_tokenizer, target_tokenizer, hn_tokenizer, lang_index=None, output=None,
+                   batch_size: Optional[int] = None):
+    """The whole driver for a PyTorch base model: surface forms of the (already byte-level) target tokenizer ->
+    prediction -> special rows -> splice -> optional save.  Mirrors ``scripts/transfer.py:204-328``.
+
+    ``target_tokenizer`` must already be byte-level with its special tokens matched to ``base_tokenizer`` (the
+    reference's ``convert_to_byte_level(..., match_special_tokens_to=base_tokenizer)``)."""
+    from .surface_forms import get_surface_form_matrix
+
+    cfg = hypernet.config
+    source_in, source_out, stacked = source_embeddings_of(base_model)
+    sfm, n_truncated = get_surface_form_matrix(target_tokenizer, cfg.hn_surface_maxlen, hn_tokenizer)
+    predict = make_predict(hypernet, stacked, lang_index)
+    if batch_size:
+        cfg_like = SimpleNamespace(hidden_size=cfg.n_embd, n_embd=cfg.n_embd)
+        pred_in, pred_out, pred_bias = batched_inference(sfm, None, cfg_like, default_args(batch_size=batch_size), predict,
+                                                         embedding_path_out=True if source_out is not None else None)
+    else:
+        pred_in, pred_out, pred_bias = predict(sfm)
+    if source_out is None:
+        pred_out = None
+    vocab = target_tokenizer.get_vocab()
+    new_ids = [vocab[t] for t in base_tokenizer.all_special_tokens]
+    overwrite_special_rows(pred_in, pred_out, pred_bias, source_in.cpu().numpy(),
+                           None if source_out is None else source_out.cpu().numpy(), base_tokenizer.all_special_ids, new_ids)
+    model = splice_into_model(base_model, pred_in, pred_out, pred_bias)
+    if output is not None:
+        base_tokenizer.save_pretrained(output)   # tokenizer_config.json and other metadata (transfer.py:281-283)
+        target_tokenizer.save_pretrained(output)
+        model.save_pretrained(output)
+    return model, dict(n_truncated=n_truncated, rows=len(sfm))
