@@ -429,59 +429,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   for (int j = 0; j < n; ++j) valid_mask |= (__ldg(p.valid + t0 + j) != 0 ? 1u : 0u) << j;
   const bool any_valid = valid_mask != 0;
   const int n_q = p.row0_only ? 1 : n;
-  constexpr int kFast = 8;  // rows of up to 8 positions (every shipped config): K and V stay in registers
-  if (n <= kFast) {
-    float kr[kFast][DPL], vr[kFast][DPL];
-#pragma unroll
-    for (int j = 0; j < kFast; ++j) {
-      if (j < n) {
-        const float* kj = p.k + static_cast<long long>(t0 + j) * p.ldk + hoff;
-        const float* vj = p.v + static_cast<long long>(t0 + j) * p.ldv + hoff;
-#pragma unroll
-        for (int d = 0; d < DPL; ++d) { kr[j][d] = __ldg(kj + 32 * d); vr[j][d] = __ldg(vj + 32 * d); }
-      }
-    }
-    for (int i = 0; i < n_q; ++i) {
-      const long long qi = p.row0_only ? r : (t0 + i);
-      float qv[DPL];
-#pragma unroll
-      for (int d = 0; d < DPL; ++d) qv[d] = __ldg(p.q + qi * p.ldq + hoff + 32 * d);
-      float sc[kFast];
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < kFast; ++j) {
-        float s = 0.f;
-        if (j < n && any_valid) {
-#pragma unroll
-          for (int d = 0; d < DPL; ++d) s += qv[d] * kr[j][d];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-          s *= p.scale;
-        }
-        const bool use = j < n && (!any_valid || ((valid_mask >> j) & 1u));
-        sc[j] = use ? s : -INFINITY;
-        m = fmaxf(m, sc[j]);
-      }
-      float l = 0.f, acc[DPL];
-#pragma unroll
-      for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
-#pragma unroll
-      for (int j = 0; j < kFast; ++j) {
-        if (j < n) {
-          const float w = expf(sc[j] - m);  // exp(-inf) = 0 for masked keys
-          l += w;
-#pragma unroll
-          for (int d = 0; d < DPL; ++d) acc[d] += w * vr[j][d];
-        }
-      }
-      const float inv = 1.0f / l;
-      const long long oi = (p.row0_only ? r : (t0 + i)) * p.ld_out + hoff;
-#pragma unroll
-      for (int d = 0; d < DPL; ++d) store_operand1(p.out_p0, p.out_p1, oi + 32 * d, acc[d] * inv, p.split_fmt);
-    }
-    return;
-  }
-  // general path (more than 8 positions per row): stream K and V per query, online softmax
+  // K and V are streamed per query (L1-resident re-reads); keeping them in registers was measured slower: the kernel is
+  // latency-bound and the register footprint cost more occupancy than the re-reads cost bandwidth
   for (int i = 0; i < n_q; ++i) {
     const long long qi = p.row0_only ? r : (t0 + i);
     float qv[DPL];
