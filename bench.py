@@ -278,20 +278,17 @@ def run_ours(args):
 
     # ---- end to end from host token strings ("e2e") -----------------------------------------------------------------
     nat.set_timing(False)
-    sf_pinned = torch.empty((rows, cfg.hn_surface_maxlen), dtype=torch.int32, pin_memory=True)
-    out_pinned = torch.empty((rows, width), dtype=torch.float32, pin_memory=True)
-    sf_dev2 = torch.empty_like(sf_dev)
+    from zett_b200.transfer import TokenPipeline
+    pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=16384)
+
+    def gather(blk):
+        if world > 1:
+            dist.all_gather_into_tensor(full, blk)                               # the single collective
 
     def e2e_step():
-        sf, _ = get_surface_form_matrix(tokens, cfg.hn_surface_maxlen, hn)     # host: native retokenizer
-        sf_pinned.numpy()[...] = sf
-        sf_dev2.copy_(sf_pinned, non_blocking=True)                              # H2D
-        nat.forward_into(sf_dev2, src, lang_i, block[:, 0:], block[:, D:] if separate else None,
-                         block[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
-        if world > 1:
-            dist.all_gather_into_tensor(full, block)                             # the single collective
-        out_pinned.copy_(block, non_blocking=True)                               # D2H of this rank's rows
-        torch.cuda.current_stream(dev).synchronize()
+        # host token strings -> native retokenizer -> pinned H2D -> forward -> (all-gather) -> pinned D2H of this rank's
+        # rows; passes are pipelined (host retokenisation and D2H of pass k overlap the compute of pass k + 1)
+        return pipe.run(tokens, after_compute=gather)
 
     e2e_step()
     sync_all()
@@ -301,7 +298,9 @@ def run_ours(args):
     sync_all()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
     e2e_value = world * rows / e2e_s
+    out_pinned, sf_e2e, _ = e2e_step()
     assert np.isfinite(out_pinned.numpy()[:, : (2 if separate else 1) * D + 1]).all()
+    assert np.array_equal(sf_e2e, sf_host)
 
     if rank != 0:
         if world > 1:

@@ -193,3 +193,91 @@ def test_full_vocab_properties_xlmr(torch_cuda):
     assert torch.equal(out[2][40000:40100], out[2][100:200])
     st = model.native().stats()
     assert st["rows"] == 50257 and st["kernel_launches"] > 0 and st["packed_positions"] > 0
+
+
+def test_pipelined_tokens_path_equals_one_shot(torch_cuda):
+    """transfer.predict_from_tokens (retokenise / H2D / compute / D2H overlapped per pass) == one-shot prediction,
+    bit for bit, including the surface forms it builds on the way."""
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    from zett_b200.surface_forms import get_surface_form_matrix
+    from zett_b200.transfer import TokenPipeline, make_predict, predict_from_tokens
+    hn = synthetic.make_hn_tokenizer("unigram", 316, seed=5, pad_token="</s>")
+    tokens = synthetic.make_target_tokens(1500, seed=6)
+    cfg, weights, model = _model(torch, "tiny", pad_token_id=int(hn.pad_token_id))
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
+    sf, n_trunc = get_surface_form_matrix(tokens, cfg.hn_surface_maxlen, hn)
+    one = make_predict(model, src)(sf)
+    piped = predict_from_tokens(model, tokens, hn, src, rows_per_pass=256)
+    for a, b in zip(one, piped):
+        np.testing.assert_array_equal(a, b)
+    pipe = TokenPipeline(model, hn, src, rows_per_pass=400)
+    out, sf2, nt2 = pipe.run(tokens)
+    np.testing.assert_array_equal(sf2, sf)
+    assert nt2 == n_trunc
+    np.testing.assert_array_equal(out[:, :cfg.n_embd].numpy(), one[0])
+
+
+@pytest.mark.parametrize("terms", [2])
+def test_fp8_correction_mode_parity(terms):
+    """split_terms = 2 (fp16 MMA + two e5m2 correction MMAs through kind::f8f6f4) meets the same 1e-3 budget."""
+    r, lines = run_selftest(["forward", "--impl", "2", "--terms", str(terms)])
+    assert len(lines) == 6, r.stdout + r.stderr
+    for ln in lines:
+        assert "error" not in ln and ln["ok"], ln
+
+
+def test_shape_variants(torch_cuda):
+    """Paths the shipped configs do not reach: 2 layers, maxlen 12 (rows longer than 8 positions), head sizes 32 and
+    128, a vocabulary of one row and an empty one."""
+    torch = torch_cuda
+    from oracle import hypernet_oracle as ho
+    from zett_b200 import synthetic
+    for overrides in (dict(hn_n_layers=2, hn_surface_maxlen=12), dict(hn_num_attention_heads=4), dict(hn_num_attention_heads=1)):
+        cfg, weights, model = _model(torch, "tiny", **overrides)
+        src_np = synthetic.make_source_embeddings(cfg, seed=12)
+        sf = synthetic.make_random_surface_forms(cfg, 77, seed=9)
+        got = model(torch.from_numpy(sf).cuda(), source_embeddings=torch.from_numpy(src_np).cuda())
+        want = ho.hypernet_forward(cfg, weights, sf, src_np)
+        masked = ho.fully_masked_rows(cfg, sf)
+        for g, w in zip(got, want):
+            fro, worst = ho.rel_errors(g.cpu().numpy(), w, exclude=masked)
+            assert fro < 1e-3 and worst < 1e-3, (overrides, fro, worst)
+    cfg, weights, model = _model(torch, "tiny")
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
+    sf = synthetic.make_random_surface_forms(cfg, 9, seed=9)
+    full = model(torch.from_numpy(sf).cuda(), source_embeddings=src)
+    one = model(torch.from_numpy(sf[4:5]).cuda(), source_embeddings=src)
+    for a, b in zip(full, one):
+        assert torch.equal(a[4:5], b)
+    empty = model(torch.zeros((0, 7), dtype=torch.int32).cuda(), source_embeddings=src)
+    assert empty[0].shape == (0, cfg.n_embd) and empty[2].shape == (0,)
+
+
+def test_full_vocab_properties_mistral(torch_cuda):
+    """BASELINE config 4 at full size (50 304 rows, Mistral-7B shape): finite, duplicate rows identical, and a slice
+    recomputed alone reproduces the whole-vocabulary result bit for bit (pass-composition invariance)."""
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    from zett_b200.modeling_hypernet import NativeHypernet
+    cfg = synthetic.make_config("mistral")
+    nat = NativeHypernet(cfg, synthetic.make_weights(cfg, seed=0), torch.device("cuda", 0))
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=100)).cuda()
+    sf = synthetic.make_random_surface_forms(cfg, 50304, seed=5)
+    sf[30000:30064] = sf[64:128]
+    sf_d = torch.from_numpy(sf).cuda()
+    D = cfg.n_embd
+    outs = [torch.empty((50304, D), device="cuda"), torch.empty((50304, D), device="cuda"), torch.empty((50304,), device="cuda")]
+    nat.forward_into(sf_d, src, -1, *outs)
+    nat.check()
+    for o in outs:
+        assert torch.isfinite(o).all()
+        assert torch.equal(o[30000:30064], o[64:128])
+    part = [torch.empty((300, D), device="cuda"), torch.empty((300, D), device="cuda"), torch.empty((300,), device="cuda")]
+    nat.forward_into(sf_d[20000:20300].contiguous(), src, -1, *part)
+    nat.check()
+    for o, p in zip(outs, part):
+        assert torch.equal(o[20000:20300], p)
+    st = nat.stats()
+    assert st["rows"] == 300 and st["distinct_ids"] > 0
+    nat.close()

@@ -206,3 +206,82 @@ def transfer_model(hypernet, base_model, base_tokenizer, target_tokenizer, hn_to
         target_tokenizer.save_pretrained(output)
         model.save_pretrained(output)
     return model, dict(n_truncated=n_truncated, rows=len(sfm))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Pipelined end-to-end path: token strings on the host -> predicted matrices in pinned host memory.
+# The vocabulary is cut into passes; while the GPU runs pass k the host retokenises pass k + 1, and the device->host
+# copy of pass k runs on a side stream under the compute of pass k + 1.  Same results as the one-shot calls (rows are
+# independent); only the overlap differs.
+# ----------------------------------------------------------------------------------------------------------------------
+class TokenPipeline:
+    """Reusable buffers + streams for ``predict_from_tokens`` (one instance per hypernet / device)."""
+
+    def __init__(self, hypernet_or_native, hn_tokenizer, source_embeddings_dev, lang_index=None, rows_per_pass: int = 16384):
+        from .surface_forms import native_model_for
+        self.nat = hypernet_or_native.native() if hasattr(hypernet_or_native, "native") else hypernet_or_native
+        self.cfg = self.nat.cfg
+        self.device = self.nat.device
+        self.src = source_embeddings_dev
+        self.lang = -1 if (lang_index is None or not self.cfg.hn_embed_lang_id) else int(lang_index)
+        self.rows_per_pass = int(rows_per_pass)
+        self.tok_model = native_model_for(hn_tokenizer)
+        self.pad_id = int(hn_tokenizer.pad_token_id)
+        self.special = {t: int(hn_tokenizer.convert_tokens_to_ids(t)) for t in hn_tokenizer.all_special_tokens}
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._cap = 0
+
+    def _ensure(self, n_rows: int, width: int):
+        if n_rows <= self._cap:
+            return
+        L = self.cfg.hn_surface_maxlen
+        self.sf_pinned = torch.empty((n_rows, L), dtype=torch.int32, pin_memory=True)
+        self.sf_dev = torch.empty((n_rows, L), dtype=torch.int32, device=self.device)
+        self.block = torch.zeros((n_rows, width), dtype=torch.float32, device=self.device)
+        self.out_pinned = torch.empty((n_rows, width), dtype=torch.float32, pin_memory=True)
+        self._cap = n_rows
+
+    def run(self, tokens, after_compute=None):
+        """Returns ``(out_pinned[:n] as [n, n_out * D + 4] fp32, surface_forms [n, L] int32, n_truncated)``; columns
+        are ``pred_in | pred_out | bias`` (``zett_b200.parallel.unpack`` splits them).  ``after_compute(block)`` runs on
+        the compute stream after the last pass (the all-gather of the multi-GPU path)."""
+        from .parallel import packed_width
+        cfg = self.cfg
+        n, D, separate = len(tokens), cfg.n_embd, bool(cfg.separate_out_embeddings)
+        width = packed_width(D, separate)
+        self._ensure(n, width)
+        stream = torch.cuda.current_stream(self.device)
+        n_trunc = 0
+        events = []
+        for lo in range(0, n, self.rows_per_pass):
+            hi = min(n, lo + self.rows_per_pass)
+            chunk = tokens[lo:hi]
+            special_ids = np.fromiter((self.special.get(t, -1) for t in chunk), dtype=np.int32, count=hi - lo)
+            sf, nt = self.tok_model.surface_forms(chunk, cfg.hn_surface_maxlen, self.pad_id, special_ids)  # host
+            n_trunc += nt
+            self.sf_pinned[lo:hi].numpy()[...] = sf
+            self.sf_dev[lo:hi].copy_(self.sf_pinned[lo:hi], non_blocking=True)                              # H2D
+            blk = self.block[lo:hi]
+            self.nat.forward_into(self.sf_dev[lo:hi], self.src, self.lang, blk[:, 0:], blk[:, D:] if separate else None,
+                                  blk[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            with torch.cuda.stream(self.copy_stream):                                                       # D2H
+                self.copy_stream.wait_event(ev)
+                self.out_pinned[lo:hi].copy_(blk, non_blocking=True)
+            events.append(ev)
+        if after_compute is not None:
+            after_compute(self.block[:n])
+        self.copy_stream.synchronize()
+        stream.synchronize()
+        return self.out_pinned[:n], self.sf_pinned[:n].numpy(), n_trunc
+
+
+def predict_from_tokens(hypernet, tokens, hn_tokenizer, source_embeddings_dev, lang_index=None, rows_per_pass: int = 16384):
+    """Token strings (byte-level spellings) -> ``(pred_in, pred_out | None, pred_bias)`` numpy arrays, pipelined."""
+    from .parallel import unpack
+    pipe = TokenPipeline(hypernet, hn_tokenizer, source_embeddings_dev, lang_index, rows_per_pass)
+    out, sf, n_trunc = pipe.run(list(tokens))
+    cfg = pipe.cfg
+    pin, pout, pbias = unpack(out, len(tokens), cfg.n_embd, bool(cfg.separate_out_embeddings))
+    return pin.numpy(), (None if pout is None else pout.numpy()), pbias.numpy()
