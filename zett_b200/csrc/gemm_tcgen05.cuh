@@ -1,16 +1,20 @@
 // Persistent, warp-specialised tcgen05 GEMM for the hypernetwork's Linear layers:
 //     out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )          (nn.Linear: y = x W^T + b, both operands K-major)
 //
-//  * operands are 16-bit "planes": plane 0 = round(x), plane 1 = round(x - plane0)  (bf16 or fp16).
-//    n_terms == 1 issues A0*B0 only; n_terms == 3 issues A0*B0 + A1*B0 + A0*B1 into the SAME TMEM accumulator,
-//    which restores ~fp32 operand precision (the 1e-3 parity budget rules out single-pass bf16).
-//  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}, 128B swizzle), warp 1 = MMA issuer + TMEM owner,
-//    warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / residual / column affine -> fp32 and/or split planes).
-//  * accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
-//    main loop of tile i+1; smem stages form an mbarrier ring.
-//  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the
-//    B tile; the leader issues the MMAs and multicasts the commits.
-//  * M may live in device memory (packed-token counts are data dependent); tiles beyond it are skipped.
+//  * operand formats (epilogue.cuh): 16-bit planes  plane 0 = round(x), plane 1 = round(x - plane 0)  issued as
+//    A0*B0 + A1*B0 + A0*B1 into the SAME TMEM accumulator (n_terms == 3; n_terms == 1 issues A0*B0 only), which restores
+//    ~fp32 operand precision (the 1e-3 parity budget rules out single-pass bf16); or fp16 + two e5m2
+//    correction planes (f8): one kind::f16 MMA + two kind::f8f6f4 MMAs per k-step.
+//  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}; 128-byte swizzle for 16-bit rows of BLOCK_K = 64, 64-byte
+//    for the fp8 planes), warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / residual /
+//    column affine -> fp32 and/or operand planes for the next GEMM).
+//  * accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the main loop of
+//    tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
+//  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the B tile; the
+//    leader alone arrives on the full barrier (expecting both CTAs' bytes), issues the MMAs and multicasts the commits.
+//  * M may live in device memory (packed-position counts are data dependent); tiles beyond it are skipped.
+//  * measured behaviour: the three-term bf16 mode keeps the tensor pipe 98-99 % active; the modes
+//    with fewer MMAs per byte are bound by operand-fetch latency x the ~190 KB of smem that can be in flight.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
