@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""CPU study of GEMM operand-precision policies against the 1e-3 parity budget ("Precision").
+
+Runs the torch oracle (test infrastructure) with ``F.linear`` replaced by a version that rounds the operands the way a
+given tensor-core operand format would, fp32 accumulation, everything else fp32 -- and reports the Frobenius / worst-row
+relative error of every output against the plain fp32 oracle.  Not part of the product or of the test-suite; it is the
+evidence behind the choice of the default ``split_terms``.
+
+usage: python scripts/precision_study.py [shape=xlmr] [rows=512]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import hypernet_oracle as ho  # noqa: E402
+from oracle import hypernet_oracle_torch as hot  # noqa: E402
+from zett_b200 import synthetic  # noqa: E402
+
+
+def r16(x, dt):
+    return x.to(dt).to(torch.float32)
+
+
+def split2(x, dt):
+    hi = r16(x, dt)
+    return hi, r16(x - hi, dt)
+
+
+class Shim:
+    """Stands in for torch.nn.functional inside the oracle module; only `linear` changes."""
+
+    def __init__(self, policy):
+        self.policy = policy
+        self.calls = 0
+
+    def __getattr__(self, name):
+        return getattr(F, name)
+
+    def linear(self, x, w, b=None):
+        mode = self.policy(self.calls, w.shape)
+        self.calls += 1
+        if mode == "exact" or w.shape[0] == 1:
+            return F.linear(x, w, b)
+        if mode == "a16":      # A fp16 single plane, W two fp16 planes (2 MMAs)
+            return F.linear(r16(x, torch.float16), w, b)
+        if mode == "w16":      # A two planes, W fp16 single plane (2 MMAs)
+            return F.linear(x, r16(w, torch.float16), b)
+        if mode == "f16":      # single pass fp16
+            return F.linear(r16(x, torch.float16), r16(w, torch.float16), b)
+        if mode == "bf16":
+            return F.linear(r16(x, torch.bfloat16), r16(w, torch.bfloat16), b)
+        if mode == "bf16x3":
+            a0, a1 = split2(x, torch.bfloat16)
+            w0, w1 = split2(w, torch.bfloat16)
+            return F.linear(a0, w0, b) + F.linear(a1, w0) + F.linear(a0, w1)
+        raise ValueError(mode)
+
+
+def run(shape, rows, policies):
+    cfg = synthetic.make_config(shape)
+    weights = synthetic.make_weights(cfg, seed=0)
+    src = synthetic.make_source_embeddings(cfg, seed=1)
+    rng = np.random.default_rng(3)
+    L = cfg.hn_surface_maxlen
+    n_ids = cfg.original_vocab_size + max(cfg.hn_n_extra_tokens, 1)
+    sf = rng.integers(0, n_ids, size=(rows, L)).astype(np.int32)
+    lens = rng.choice(np.arange(1, L + 1), size=rows, p=np.array([3, 14, 8, 4, 2, 1, 1.5]) / 33.5)
+    for i, n in enumerate(lens):
+        sf[i, n:] = cfg.pad_token_id
+    W = hot.to_torch(weights)
+    srct = torch.from_numpy(src)
+    lang = 3 if cfg.hn_embed_lang_id else None
+    ref = hot.hypernet_forward(cfg, W, sf, srct, lang_index=lang)
+    masked = ho.fully_masked_rows(cfg, sf)
+    for name, pol in policies.items():
+        hot.F = Shim(pol)
+        try:
+            got = hot.hypernet_forward(cfg, W, sf, srct, lang_index=lang)
+        finally:
+            n_calls = hot.F.calls
+            hot.F = F
+        errs = []
+        for g, r in zip(got, ref):
+            if r is None:
+                continue
+            errs.append(ho.rel_errors(g, r, exclude=masked))
+        print("%-28s gemms=%d  " % (name, n_calls) + "  ".join("fro %.2e worst %.2e" % e for e in errs), flush=True)
+
+
+def main():
+    shape = sys.argv[1] if len(sys.argv) > 1 else "xlmr"
+    rows = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+    torch.set_num_threads(os.cpu_count())
+    # GEMM call order in the oracle: 0 in_proj0, 1-2 in_proj1, per layer l: 3+6l.. q k v o inter out, 21-23 head_in, 24-26 head_out
+    enc = set(range(3, 21))
+    policies = {
+        "bf16x3 (default)": lambda i, s: "bf16x3",
+        "a16 everywhere": lambda i, s: "a16",
+        "w16 everywhere": lambda i, s: "w16",
+        "f16 single pass": lambda i, s: "f16",
+        "a16 encoder, bf16x3 rest": lambda i, s: "a16" if i in enc else "bf16x3",
+        "a16 except heads": lambda i, s: "a16" if i < 21 else "bf16x3",
+        "a16 except in_proj+heads": lambda i, s: "a16" if 3 <= i < 21 else "bf16x3",
+        "a16 only MLP up/down": lambda i, s: "a16" if (i in enc and (i - 3) % 6 >= 4) else "bf16x3",
+    }
+    run(shape, rows, policies)
+
+
+if __name__ == "__main__":
+    main()

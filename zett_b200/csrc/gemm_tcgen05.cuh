@@ -12,9 +12,14 @@
 //    tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
 //  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the B tile; the
 //    leader alone arrives on the full barrier (expecting both CTAs' bytes), issues the MMAs and multicasts the commits.
+//  * CP == 2 puts two such pairs in one cluster of four CTAs working on vertically adjacent 256-row tiles of the same
+//    N tile: every CTA fetches only HALF of its pair's share of the W tile and TMA-multicasts it to the CTA holding the
+//    same share in the other pair (.multicast::cluster), so a cluster moves 4 A blocks + 2 W blocks through L2 -> SM
+//    instead of 4 + 4.  The kernel is bound by L2 slice throughput (~6.5 KB/clk chip-wide), so the
+//    25 % fewer bytes are what lets the formats with fewer MMAs per byte reach the tensor pipe.  A smem stage of a CTA is
+//    then written by two CTAs, so every empty barrier counts one tcgen05.commit from EACH pair leader (multicast to all
+//    four CTAs); the full barriers stay per pair.
 //  * M may live in device memory (packed-position counts are data dependent); tiles beyond it are skipped.
-//  * measured behaviour: the three-term bf16 mode keeps the tensor pipe 98-99 % active; the modes
-//    with fewer MMAs per byte are bound by operand-fetch latency x the ~190 KB of smem that can be in flight.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -36,7 +41,6 @@ struct GemmShape {
   int block_n;         // 32, 64, 128 or 256
   int group_m;         // rasterisation: m-tiles per group
   int chunk_n;         // rasterisation: n-tiles per L2-resident W chunk
-  int prefetch_dist;   // k-blocks the L2 prefetch runs ahead of the demand loads (0 = off)
   int block_k;         // K elements per pipeline stage: 64 (128-byte rows of 16-bit operands) or 32
   int n_terms;         // 1 or 3
   int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
@@ -71,11 +75,14 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_til
   return t;
 }
 
-template <int CG>
+// tmap_a / tmap_a8: box {block_k, 128 rows, all planes};  tmap_b / tmap_b8: box {block_k, block_n / (CG * CP) rows,
+// all planes (CP == 1) or ONE plane (CP == 2: a multicast share lands inside each plane of the [plane][row] smem layout)}
+template <int CG, int CP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a8, const __grid_constant__ CUtensorMap tmap_b8,
                     const GemmShape s, const EpilogueParams ep) {
+  static_assert(CP == 1 || CG == 2, "pairs of pairs need cta_group::2");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -88,18 +95,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cluster_rank = (CG * CP > 1) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & (CG - 1);   // rank inside the CTA pair (cta_group::2 pairs ranks 2p, 2p + 1)
+  const uint32_t pair = cluster_rank / CG;             // pair inside the cluster
   const bool leader = cta_rank == 0;
 
   const int M = s.m_dev ? *s.m_dev : s.m_host;
-  const int tile_m = kBlockM * CG;
+  const int tile_m = kBlockM * CG * CP;                // rows of one cluster tile
   const int m_tiles = (M + tile_m - 1) / tile_m;
   const int n_tiles = (s.n + s.block_n - 1) / s.block_n;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (s.k + s.block_k - 1) / s.block_k;
-  const int first_tile = blockIdx.x / CG;
-  const int tile_step = gridDim.x / CG;
-  const int load_n = s.block_n / CG;  // rows of the W tile this CTA stages
+  const int first_tile = blockIdx.x / (CG * CP);
+  const int tile_step = gridDim.x / (CG * CP);
+  const int load_n = s.block_n / CG;  // rows of the W tile this CTA's smem holds
+  const int cta_row0 = static_cast<int>(pair) * kBlockM * CG + static_cast<int>(cta_rank) * kBlockM;  // inside the cluster tile
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -109,8 +119,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       prefetch_tmap(&tmap_b8);
     }
     for (int i = 0; i < s.num_stages; ++i) {
-      mbar_init(full_bar(i), 1);    // the leader's arrive.expect_tx covers the bytes of every CTA of the group
-      mbar_init(empty_bar(i), 1);   // one tcgen05.commit
+      mbar_init(full_bar(i), 1);    // the leader's arrive.expect_tx covers the bytes landing in both CTAs of the pair
+      mbar_init(empty_bar(i), CP);  // one tcgen05.commit per pair that reads or multicasts into this stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar(i), 1);
@@ -120,7 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (CG * CP > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -130,35 +140,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // L2 prefetch cursor: walks the same (tile, k-block) sequence `prefetch_dist` steps ahead of the demand loads.
-      // The main loop is bound by fetch latency x the ~190 KB of smem that can be in flight; a DRAM miss in any line
-      // of a stage delays the whole stage, so the misses are taken early, by requests that need no smem.
-      int pf_tile = first_tile, pf_kb = 0, pf_row_a = 0, pf_row_b = 0;
-      auto pf_rows = [&]() {
-        if (pf_tile < total_tiles) {
-          const TileCoord pc = tile_coord(pf_tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
-          pf_row_a = pc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
-          pf_row_b = pc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
-        }
-      };
-      auto pf_step = [&]() {
-        if (pf_tile >= total_tiles) return;
-        tma_prefetch_3d(&tmap_a, pf_kb * s.block_k, pf_row_a, 0);
-        tma_prefetch_3d(&tmap_b, pf_kb * s.block_k, pf_row_b, 0);
-        if (s.f8) {
-          tma_prefetch_3d(&tmap_a8, pf_kb * s.block_k, pf_row_a, 0);
-          tma_prefetch_3d(&tmap_b8, pf_kb * s.block_k, pf_row_b, 0);
-        }
-        if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += tile_step; pf_rows(); }
-      };
-      pf_rows();
-      for (int i = 0; i < s.prefetch_dist; ++i) pf_step();
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
-        const int row_a = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
+        const int row_a = tc.m_blk * tile_m + cta_row0;
         const int row_b = tc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (s.prefetch_dist > 0) pf_step();
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
           const uint32_t a_dst = smem_base + stage * s.stage_bytes;
           const uint32_t b_dst = a_dst + s.n_planes * s.a_plane_bytes;
@@ -173,15 +159,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
             }
           } else {
-            // only the leader arrives (expecting both CTAs' bytes); the peer's copies credit the leader's barrier
-            // directly, so the peer's loop carries no cluster-scope operation.  Its bytes may land before the
+            // only the leader arrives (expecting the bytes landing in both CTAs of its pair); the other copies credit
+            // that barrier directly, so no other loop carries a cluster-scope operation.  Bytes may land before the
             // leader's expect_tx: the phase cannot complete until that arrive, and the transaction count is signed.
             if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
             tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0);
-            tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0);
-            if (s.f8) {
-              tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * s.block_k, row_a, 0);
-              tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
+            if (s.f8) tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * s.block_k, row_a, 0);
+            if constexpr (CP == 1) {
+              tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0);
+              if (s.f8) tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
+            } else {
+              // this CTA fetches rows [pair * load_n / 2, +load_n / 2) of its share, plane by plane, for itself and for the
+              // CTA of equal pair rank in the other pair; the other half arrives from there.  Each copy credits the full
+              // barrier of the destination's own pair leader.
+              const int share = load_n / CP;
+              const int row_s = row_b + static_cast<int>(pair) * share;
+              const uint16_t mask = static_cast<uint16_t>(0x5u << cta_rank);
+              const uint32_t off16 = pair * static_cast<uint32_t>(share) * static_cast<uint32_t>(s.block_k) * 2u;
+              for (int pl = 0; pl < s.n_planes; ++pl)
+                tma_load_3d_2sm_mc(&tmap_b, full_bar(stage), b_dst + pl * s.b_plane_bytes + off16, kb * s.block_k, row_s, pl, mask);
+              if (s.f8) {
+                const uint32_t off8 = off16 >> 1;
+                for (int pl = 0; pl < 2; ++pl)
+                  tma_load_3d_2sm_mc(&tmap_b8, full_bar(stage), b8_dst + pl * s.b8_plane_bytes + off8, kb * s.block_k, row_s, pl, mask);
+              }
             }
           }
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
@@ -191,6 +192,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
     if (lane == 0 && leader) {
+      const uint16_t kAllMask = static_cast<uint16_t>((1u << (CG * CP)) - 1u);
+      const uint16_t kPairMask = static_cast<uint16_t>(((1u << CG) - 1u) << (pair * CG));
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -228,8 +231,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (int kk = 0; kk < s.block_k / 32; ++kk) umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, 1u);
             }
           }
-          umma_commit<CG>(empty_bar(stage));                       // frees the smem stage (both CTAs)
-          if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc));  // accumulator complete
+          umma_commit<CG>(empty_bar(stage), kAllMask);                      // frees the stage in every CTA of the cluster
+          if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc), kPairMask);  // accumulator complete (this pair)
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -244,7 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t acc_phase = (iter >> 1) & 1u;
       mbar_wait(tmem_full_bar(acc), acc_phase, 4);
       tc_fence_after();
-      const int row = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM + quarter * 32 + lane;
+      const int row = tc.m_blk * tile_m + cta_row0 + quarter * 32 + lane;
       const int col_tile = tc.n_blk * s.block_n;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
       // two register chunks: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed
@@ -263,13 +266,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tc_fence_before();
       if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
-      else mbar_arrive_cluster(tmem_empty_bar(acc), 0);
+      else mbar_arrive_cluster(tmem_empty_bar(acc), pair * CG);
     }
   }
 
   __syncwarp();
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (CG * CP > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
 }
 

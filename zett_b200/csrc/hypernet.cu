@@ -65,18 +65,18 @@ int get_encode_fn(EncodeTiledFn* out) {
   return ZETT_OK;
 }
 
-// 3-D map {K, rows, planes} over 16-bit planes, box {64, box_rows, n_planes}, 128-byte swizzle, zero fill out of bounds
+// 3-D map {K, rows, planes} over 16-bit planes, box {block_k, box_rows, box_planes}, 128-byte swizzle, zero fill out of bounds
 CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long long k, long long plane_stride_elems,
-                    int box_rows, int n_planes, int split_fmt, int block_k) {
+                    int box_rows, int n_planes, int box_planes, int split_fmt, int block_k) {
   EncodeTiledFn enc;
   ZETT_TRY(get_encode_fn(&enc));
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(n_planes)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(k) * 2u, static_cast<cuuint64_t>(plane_stride_elems) * 2u};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(n_planes)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_planes)};
   cuuint32_t estr[3] = {1, 1, 1};
   if (n_planes == 1) strides[1] = strides[0] * static_cast<cuuint64_t>(rows);
   const CUtensorMapDataType dt = split_fmt == kFmtBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -93,12 +93,12 @@ int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long
 
 // 3-D map {K, rows, 2} over the two e5m2 correction planes, box {64, box_rows, 2}, 64-byte swizzle
 int make_plane8_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long k, long long plane_stride_bytes,
-                     int box_rows, int block_k) {
+                     int box_rows, int box_planes, int block_k) {
   EncodeTiledFn enc;
   ZETT_TRY(get_encode_fn(&enc));
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), 2};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(plane_stride_bytes)};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_planes)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -152,8 +152,9 @@ int set_kernel_attrs(DeviceInfo* d) {
   unsigned long long* dptr = nullptr;
   ZETT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_watchdog_host, 0));
   ZETT_CUDA(cudaMemcpyToSymbol(g_zett_watchdog, &dptr, sizeof dptr));
-  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   ZETT_CUDA(cudaFuncSetAttribute(gather_rescale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
   d->attrs_set = true;
   return ZETT_OK;
@@ -176,14 +177,14 @@ struct GemmArgs {
 
 struct GemmEngine {
   DeviceInfo dev;
-  int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 2-CTA, 3: SIMT
+  int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 CTA pairs, 3: SIMT, 4: CTA pairs, two per cluster, W multicast
+  int max_clusters4 = -1;  // co-resident clusters of four CTAs (queried once; GPC sizes decide it)
   int n_terms = 3;     // 3: 16-bit three-term split, 1: single 16-bit pass, 2: fp16 + two e5m2 correction passes
   int split_fmt = kFmtBf16;
   std::map<std::tuple<const void*, long long, long long, long long, int, int>, CUtensorMap> tmaps;
   void read_env() {
     if (const char* e = getenv("ZETT_RASTER_CHUNK_MB")) raster_chunk_bytes = std::max(1ll, atoll(e)) << 20;
     if (const char* e = getenv("ZETT_RASTER_GROUP_M")) raster_group_m = std::max(1, atoi(e));
-    if (const char* e = getenv("ZETT_PREFETCH_DIST")) prefetch_dist = std::max(0, atoi(e));
     if (const char* e = getenv("ZETT_BLOCK_K")) block_k = atoi(e) == 32 ? 32 : 64;
   }
   void set_precision(int terms) {
@@ -194,7 +195,6 @@ struct GemmEngine {
   // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
   long long raster_chunk_bytes = 48ll << 20;
   int raster_group_m = 4;
-  int prefetch_dist = 0;   // L2 prefetch ahead of the demand loads: measured to hurt (doubles DRAM reads), kept as a knob
   int block_k = 64;        // K per pipeline stage (64 or 32)
   bool timing = false;
   std::vector<cudaEvent_t> events;
@@ -223,23 +223,25 @@ struct GemmEngine {
   }
 
   int tmap(const uint16_t* base, long long rows, long long k, long long plane_stride, int box_rows, int n_planes,
-           const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k, n_planes);
+           int box_planes, const CUtensorMap** out) {
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k,
+                               n_planes + 16 * box_planes);
     auto it = tmaps.find(key);
     if (it == tmaps.end()) {
       CUtensorMap m;
-      ZETT_TRY(make_plane_tmap(&m, base, rows, k, plane_stride, box_rows, n_planes, split_fmt, block_k));
+      ZETT_TRY(make_plane_tmap(&m, base, rows, k, plane_stride, box_rows, n_planes, box_planes, split_fmt, block_k));
       it = tmaps.emplace(key, m).first;
     }
     *out = &it->second;
     return ZETT_OK;
   }
-  int tmap8(const uint8_t* base, long long rows, long long k, long long plane_stride, int box_rows, const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k, 8);
+  int tmap8(const uint8_t* base, long long rows, long long k, long long plane_stride, int box_rows, int box_planes,
+            const CUtensorMap** out) {
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k, 8 + 16 * box_planes);
     auto it = tmaps.find(key);
     if (it == tmaps.end()) {
       CUtensorMap m;
-      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, plane_stride, box_rows, block_k));
+      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, plane_stride, box_rows, box_planes, block_k));
       it = tmaps.emplace(key, m).first;
     }
     *out = &it->second;
@@ -273,6 +275,7 @@ struct GemmEngine {
       return ZETT_OK;
     }
     const int cg = impl == 1 ? 1 : 2;
+    const int cp = impl == 4 ? 2 : 1;   // CTA pairs per cluster
     GemmShape s{};
     s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
     s.block_n = pick_block_n(g.n);
@@ -292,37 +295,54 @@ struct GemmEngine {
     s.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | shape_bits;
     s.idesc8 = (1u << 4) | (1u << 7) | (1u << 10) | shape_bits;  // kind::f8f6f4: A, B = E5M2 (1), D = F32
     const CUtensorMap *ta, *tb, *ta8, *tb8;
-    ZETT_TRY(tmap(g.a, g.a_rows, g.k, g.a_plane_stride, kBlockM, n_planes, &ta));
-    ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n, n_planes, &tb));
+    // with two pairs per cluster a CTA fetches half of its W share, one plane per copy (gemm_tcgen05.cuh)
+    ZETT_TRY(tmap(g.a, g.a_rows, g.k, g.a_plane_stride, kBlockM, n_planes, n_planes, &ta));
+    ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n / cp, n_planes, cp == 2 ? 1 : n_planes, &tb));
     ta8 = ta; tb8 = tb;
     if (f8) {
-      ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, g.a_plane_stride, kBlockM, &ta8));
-      ZETT_TRY(tmap8(g.w_q, g.n, g.k, g.w_plane_stride, load_n, &tb8));
+      ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, g.a_plane_stride, kBlockM, 2, &ta8));
+      ZETT_TRY(tmap8(g.w_q, g.n, g.k, g.w_plane_stride, load_n / cp, cp == 2 ? 1 : 2, &tb8));
     }
-    const int tile_m = kBlockM * cg;
+    const int tile_m = kBlockM * cg * cp;
     const long long m_tiles = (g.m_host + tile_m - 1) / tile_m;
     const long long n_tiles = (g.n + s.block_n - 1) / s.block_n;
     // W chunk of <= ~48 MB (4 bytes per element in every multi-plane format) stays in the 126 MB L2 next to the A group
     const long long w_tile_bytes = static_cast<long long>(s.block_n) * g.k * (n_terms == 1 ? 2 : 4);
     s.chunk_n = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, raster_chunk_bytes / std::max<long long>(w_tile_bytes, 1))));
-    s.group_m = raster_group_m;
-    s.prefetch_dist = prefetch_dist;
+    s.group_m = std::max(1, raster_group_m / cp);
     const long long tiles = m_tiles * n_tiles;
     if (tiles == 0) return ZETT_OK;
-    int ctas = static_cast<int>(std::min<long long>(dev.num_sms / cg, tiles)) * cg;
     const size_t smem = static_cast<size_t>(s.num_stages) * s.stage_bytes + kGemmSmemSlack;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(ctas);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cg * cp; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    int clusters = dev.num_sms / (cg * cp);
+    if (cp == 2) {
+      // clusters of four must sit inside one GPC: the number that can be co-resident depends on the GPC sizes of this
+      // die, and a persistent grid larger than that would serialise whole clusters behind the others
+      if (max_clusters4 < 0) {
+        cfg.gridDim = dim3((dev.num_sms / 4) * 4);
+        cfg.dynamicSmemBytes = kMaxDynSmem;
+        int n = 0;
+        ZETT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<2, 2>, &cfg));
+        cfg.dynamicSmemBytes = smem;
+        if (n < 1) return fail(ZETT_ERR_CUDA, "no cluster of four CTAs can be resident on this device");
+        max_clusters4 = n;
+        if (getenv("ZETT_VERBOSE")) fprintf(stderr, "[zett] co-resident clusters of 4: %d (of %d SMs)\n", n, dev.num_sms);
+      }
+      clusters = std::min(clusters, max_clusters4);
+    }
+    const int ctas = static_cast<int>(std::min<long long>(clusters, tiles)) * cg * cp;
+    cfg.gridDim = dim3(ctas);
     ZETT_TRY(time_mark(stream));
-    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, *ta, *tb, *ta8, *tb8, s, g.ep));
-    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, *ta, *tb, *ta8, *tb8, s, g.ep));
+    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 1>, *ta, *tb, *ta8, *tb8, s, g.ep));
+    else if (cp == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 1>, *ta, *tb, *ta8, *tb8, s, g.ep));
+    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 2>, *ta, *tb, *ta8, *tb8, s, g.ep));
     ZETT_TRY(time_mark(stream));
     return ZETT_OK;
   }
@@ -918,7 +938,7 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   int impl = cfg->gemm_impl;
   if (const char* e = getenv("ZETT_GEMM_IMPL")) impl = atoi(e);
   h->gemm.impl = impl == 0 ? 2 : impl;
-  if (h->gemm.impl < 1 || h->gemm.impl > 3) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..3"); }
+  if (h->gemm.impl < 1 || h->gemm.impl > 4) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..4"); }
   int terms = cfg->split_terms;
   if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
   h->gemm.set_precision(terms);

@@ -104,10 +104,15 @@ __device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t bar, 
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// prefetch one box of a tiled tensor into L2 (no smem, no barrier): turns the later demand load into an L2 hit
-__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+// 2-CTA multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` (cluster ranks), and each
+// destination's bytes are credited to the barrier at `bar`'s offset in the leader of THAT CTA's pair
+__device__ __forceinline__ void tma_load_3d_2sm_mc(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 // 1-D bulk copy global -> smem (gather of whole embedding rows)
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -169,13 +174,12 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64
   }
 }
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies fence::before_thread_sync).
-// CG == 2: the arrive is multicast to the same barrier offset in both CTAs of the pair.
+// CG == 2: the arrive is multicast to the same barrier offset in every CTA of `mask` (cluster ranks).
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t mask) {
   if constexpr (CG == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
   } else {
-    const uint16_t mask = 0x3;
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
   }
