@@ -71,8 +71,9 @@ typedef struct zett_hn_config {
   float encoder_layer_norm_eps;            /* 1e-5 (roberta-base)                                                  */
   /* execution knobs, not model semantics */
   int32_t max_rows_per_pass;               /* rows handled by one pass of the kernels (0 -> 16384, transfer.py:44) */
-  int32_t gemm_impl;                       /* 0 = auto (tcgen05 2-CTA), 1 = tcgen05 1-CTA, 2 = tcgen05 2-CTA,
-                                              3 = SIMT fp32 debug kernel (checker, never the default)              */
+  int32_t gemm_impl;                       /* 0 = auto, 1 = tcgen05 1-CTA, 2 = tcgen05 CTA pairs (cta_group::2),
+                                              3 = SIMT fp32 debug kernel (checker, never the default),
+                                              4 = CTA pairs, two per cluster, W tile TMA-multicast between them     */
   int32_t split_terms;                     /* operand precision: 0/3 = three bf16 MMA terms (A0W0 + A1W0 + A0W1),
                                               2 = fp16 MMA + two e5m2 correction MMAs at fp8 rate, 1 = one bf16 pass
                                               (1 misses the 1e-3 parity budget; for comparison only)               */
@@ -125,6 +126,8 @@ typedef struct zett_hn_stats {
   double gemm_ms;              /* summed CUDA-event time of the GEMM kernel launches (only with zett_hn_set_timing) */
   int64_t gemm_launches;
   int64_t distinct_ids;        /* distinct surface-form ids summed over the passes (input projection runs per id)  */
+  int64_t distinct_pairs;      /* distinct (id, position) pairs summed over the passes (first encoder layer's
+                                  LayerNorm and query/key/value GEMM run per pair); 0 when that is switched off    */
 } zett_hn_stats;
 int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out);
 

@@ -111,6 +111,87 @@ def run_sweep():
     return True
 
 
+class PowerSampler:
+    """nvidia-smi power / SM clock every 100 ms (GPU 0)."""
+
+    def __init__(self):
+        import subprocess
+        import tempfile
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw,temperature.gpu",
+                                      "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(self.path, "w"),
+                                     stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        self.proc.terminate()
+        self.proc.wait(timeout=5)
+        rows = []
+        for ln in open(self.path):
+            try:
+                rows.append([float(x) for x in ln.split(",")])
+            except ValueError:
+                pass
+        os.unlink(self.path)
+        rows = rows[len(rows) // 3:]  # steady state: drop the ramp
+        if not rows:
+            return {}
+        a = np.array(rows)
+        return dict(sm_mhz=float(np.median(a[:, 0])), power_w=float(np.median(a[:, 1])), temp_c=float(a[:, 2].max()), samples=len(a))
+
+
+def run_sustained(mnk_list, seconds=1.5):
+    """Energy / throughput probes (no parity claim): every operand format and cluster shape launched back to back for
+    ~`seconds`, with board power and SM clock sampled meanwhile; ZETT_MMA_MASK variants drop product terms to separate the
+    cost of the MMAs from the cost of moving the operands.  A cuBLAS bf16 matmul of the same shape runs beside them."""
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    for (m, n, k) in mnk_list:
+        a = torch.randn(m, k, device=dev)
+        w = torch.randn(n, k, device=dev) / k ** 0.5
+        out = torch.empty((m, n), device=dev)
+        variants = [(impl, terms, mask) for impl in (2, 4) for (terms, mask) in ((3, 7), (3, 1), (2, 7), (2, 1), (2, 4), (1, 7))]
+        for (impl, terms, mask) in variants:
+            os.environ["ZETT_MMA_MASK"] = str(mask)
+            ms = ctypes.c_float(0)
+            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, 0, impl, terms, 2,
+                                         ctypes.byref(ms), None))
+            iters = max(4, int(seconds * 1e3 / max(ms.value / 2, 1e-3)))
+            ps = PowerSampler()
+            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, 0, impl, terms, iters,
+                                         ctypes.byref(ms), None))
+            st = ps.stop()
+            t = ms.value / iters
+            print(json.dumps(dict(kind="sustained", m=m, n=n, k=k, impl=impl, terms=terms, mma_mask=mask, iters=iters,
+                                  ms=round(t, 4), tflops_once=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), **st)), flush=True)
+        os.environ.pop("ZETT_MMA_MASK", None)
+        ab, wb = a.bfloat16(), w.bfloat16()
+        ob = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.matmul(ab, wb.T, out=ob)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            torch.matmul(ab, wb.T, out=ob)
+        e1.record()
+        torch.cuda.synchronize()
+        iters = max(4, int(seconds * 1e3 / (e0.elapsed_time(e1) / 4)))
+        ps = PowerSampler()
+        e0.record()
+        for _ in range(iters):
+            torch.matmul(ab, wb.T, out=ob)
+        e1.record()
+        torch.cuda.synchronize()
+        st = ps.stop()
+        t = e0.elapsed_time(e1) / iters
+        print(json.dumps(dict(kind="sustained", m=m, n=n, k=k, impl="cublas_bf16", iters=iters, ms=round(t, 4),
+                              tflops_once=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), **st)), flush=True)
+        del a, w, out, ab, wb, ob
+    return True
+
+
 def run_one(m, n, k, impl, terms):
     lib = _lib.load()
     dev = torch.device("cuda", 0)
@@ -193,7 +274,7 @@ FORWARD_CASES = {
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["gemm", "forward", "sweep", "one"])
+    ap.add_argument("what", choices=["gemm", "forward", "sweep", "one", "sustained"])
     ap.add_argument("--mnk", default="16384,4096,4096")
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--configs", default="tiny,tiny_lang,tiny_single_head,tiny_plain,tiny_one_layer,tiny_multi_pass")
@@ -204,6 +285,8 @@ def main():
         ok = run_one(m, n, k, args.impl or 2, args.terms or 3)
     elif args.what == "sweep":
         ok = run_sweep()
+    elif args.what == "sustained":
+        ok = run_sustained([tuple(int(x) for x in t.split(",")) for t in args.mnk.split(";")])
     elif args.what == "gemm":
         ok = run_gemm(args.impl or 2)
     else:

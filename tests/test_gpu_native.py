@@ -281,3 +281,40 @@ def test_full_vocab_properties_mistral(torch_cuda):
     st = nat.stats()
     assert st["rows"] == 300 and st["distinct_ids"] > 0
     nat.close()
+
+
+@pytest.mark.parametrize("name,lang", [("tiny", None), ("tiny_lang", 2)])
+def test_pair_dedup_is_bit_exact(torch_cuda, name, lang, monkeypatch):
+    """The first encoder layer evaluated once per distinct (id, position) pair must reproduce the per-position
+    evaluation bit for bit (same arithmetic on the same operands), with and without the lang-id slot, over several
+    passes; the statistics report fewer pairs than positions on a vocabulary with repeated pieces."""
+    torch = torch_cuda
+    from zett_b200 import synthetic
+    from zett_b200.modeling_hypernet import NativeHypernet
+    cfg = synthetic.make_config(name)
+    weights = synthetic.make_weights(cfg, seed=11)
+    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
+    sf = synthetic.make_random_surface_forms(cfg, 700, seed=21)
+    sf[:, 0] = sf[:, 0] % 7  # few distinct (id, position 0) pairs
+    sf_d = torch.from_numpy(sf).cuda()
+    D = cfg.n_embd
+    results = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ZETT_DEDUP_PAIRS", flag)
+        nat = NativeHypernet(cfg, weights, torch.device("cuda", 0), max_rows_per_pass=256)
+        outs = [torch.full((700, D), float("nan"), device="cuda"),
+                torch.full((700, D), float("nan"), device="cuda") if cfg.separate_out_embeddings else None,
+                torch.full((700,), float("nan"), device="cuda")]
+        nat.forward_into(sf_d, src, -1 if lang is None else lang, *outs)
+        nat.check()
+        st = nat.stats()
+        if flag == "1":
+            assert 0 < st["distinct_pairs"] < st["encoder_positions"], st
+        else:
+            assert st["distinct_pairs"] == 0, st
+        results.append(outs)
+        nat.close()
+    for a, b in zip(*results):
+        if a is not None:
+            assert torch.isfinite(a).all()
+            assert torch.equal(a, b)

@@ -45,6 +45,7 @@ struct GemmShape {
   int n_terms;         // 1 or 3
   int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
   int f8;              // 1: operand format kFmtF16F8 -- one fp16 plane + two e5m2 correction planes (epilogue.cuh)
+  int mma_mask;        // diagnostic (ZETT_MMA_MASK, default 7): bit 0 main term, bit 1 16-bit correction terms, bit 2 fp8 terms
   uint32_t idesc;      // tcgen05 instruction descriptor (kind::f16)
   uint32_t idesc8;     // tcgen05 instruction descriptor (kind::f8f6f4), f8 only
   int num_stages;
@@ -215,13 +216,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 4
           for (int kk = 0; kk < ksteps; ++kk) {
             const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
-            umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
-            if (s.n_terms == 3 && !s.f8) {
+            if (s.mma_mask & 1) umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
+            if (s.n_terms == 3 && !s.f8 && (s.mma_mask & 2)) {
               umma_f16<CG>(tmem_d, da1 + koff, db0 + koff, s.idesc, 1u);
               umma_f16<CG>(tmem_d, da0 + koff, db1 + koff, s.idesc, 1u);
             }
           }
-          if (s.f8) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
+          if (s.f8 && (s.mma_mask & 4)) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
             const uint32_t a8 = b0 + s.n_planes * s.b_plane_bytes;
             const uint32_t b8 = a8 + 2u * s.a8_plane_bytes;
 #pragma unroll

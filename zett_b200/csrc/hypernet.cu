@@ -186,6 +186,7 @@ struct GemmEngine {
     if (const char* e = getenv("ZETT_RASTER_CHUNK_MB")) raster_chunk_bytes = std::max(1ll, atoll(e)) << 20;
     if (const char* e = getenv("ZETT_RASTER_GROUP_M")) raster_group_m = std::max(1, atoi(e));
     if (const char* e = getenv("ZETT_BLOCK_K")) block_k = atoi(e) == 32 ? 32 : 64;
+    if (const char* e = getenv("ZETT_MMA_MASK")) mma_mask = atoi(e) & 7;  // energy / throughput probes only: results are wrong
   }
   void set_precision(int terms) {
     n_terms = (terms == 1 || terms == 2) ? terms : 3;
@@ -196,6 +197,7 @@ struct GemmEngine {
   long long raster_chunk_bytes = 48ll << 20;
   int raster_group_m = 4;
   int block_k = 64;        // K per pipeline stage (64 or 32)
+  int mma_mask = 7;        // diagnostic: which product terms are issued (gemm_tcgen05.cuh)
   bool timing = false;
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
@@ -279,7 +281,7 @@ struct GemmEngine {
     GemmShape s{};
     s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
     s.block_n = pick_block_n(g.n);
-    s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0;
+    s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0; s.mma_mask = mma_mask;
     const int load_n = s.block_n / cg;
     s.block_k = block_k;
     s.a_plane_bytes = kBlockM * block_k * 2;
@@ -446,7 +448,8 @@ struct Workspace {
   // pack metadata
   int *counts_all = nullptr, *row_start1 = nullptr, *row_start2 = nullptr, *tok_src = nullptr, *tok_pos = nullptr,
       *tok_enc = nullptr, *tok1_row = nullptr, *lang_enc = nullptr, *tok2_row = nullptr, *id_claim = nullptr,
-      *id_slot = nullptr, *uniq_src = nullptr, *tok_u = nullptr;
+      *id_slot = nullptr, *uniq_src = nullptr, *tok_u = nullptr, *pair_claim = nullptr, *pair_slot = nullptr,
+      *pair_u = nullptr, *pair_pos = nullptr, *enc_pair = nullptr;
   long long uniq_cap = 0;
   unsigned char* tok2_valid = nullptr;
   // position-indexed buffers
@@ -480,7 +483,8 @@ struct zett_hn {
   // statistics
   long long passes = 0;
   zett_hn_stats stats{};
-  double coef_t1 = 0, coef_t2 = 0, coef_rows = 0, coef_u = 0;  // FLOPs per surface position / encoder position / row / distinct id
+  double coef_t1 = 0, coef_t2 = 0, coef_rows = 0, coef_u = 0, coef_p = 0;  // FLOPs per surface position / encoder position / row / distinct id / distinct pair
+  bool dedup_pairs = true;     // first encoder layer: LayerNorm + query/key/value once per distinct (id, position) pair
 };
 
 namespace {
@@ -510,6 +514,7 @@ size_t workspace_bytes_for(const zett_hn* h, long long rows) {
   size_t b = 0;
   const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
   b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 6 * t1 + rows + t2 + 2 * n_ids) + t2;
+  b += sizeof(int) * (2 * std::min<long long>(t1, n_ids) * h->L + 2 * (t1 + 1) + t2);  // distinct (id, position) pairs
   b += 2ull * 2 * std::min<long long>(t1, n_ids) * E;  // P_E
   b += 2ull * 2 * t2 * H * 2;             // PH_a, PH_b
   b += 2ull * 2 * t2 * I;                 // PI
@@ -541,6 +546,11 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.id_slot, n_ids);
   WS_ALLOC(w.uniq_src, w.uniq_cap);
   WS_ALLOC(w.tok_u, t1);
+  WS_ALLOC(w.pair_claim, w.uniq_cap * h->L);
+  WS_ALLOC(w.pair_slot, w.uniq_cap * h->L);
+  WS_ALLOC(w.pair_u, t1 + 1);
+  WS_ALLOC(w.pair_pos, t1 + 1);
+  WS_ALLOC(w.enc_pair, t2);
   WS_ALLOC(w.P_E, 2 * w.uniq_cap * E);
   WS_ALLOC(w.PH_a, 2 * t2 * H);
   WS_ALLOC(w.PH_b, 2 * t2 * H);
@@ -665,9 +675,11 @@ int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
   return ZETT_OK;
 }
 
-enum MClass { kMSurface, kMEncoder, kMRows, kMUnique };
+enum MClass { kMSurface, kMEncoder, kMRows, kMUnique, kMPairs };
 
-int count_slot(MClass m) { return m == kMSurface ? kCntSurface : (m == kMEncoder ? kCntEncoder : kCntUnique); }
+int count_slot(MClass m) {
+  return m == kMSurface ? kCntSurface : (m == kMEncoder ? kCntEncoder : (m == kMPairs ? kCntPairs : kCntUnique));
+}
 
 // One Linear layer through the GEMM engine.  `a` / `out_*` are plane-0 pointers; `cap` = rows the buffers hold.
 int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const uint16_t* a, long long cap, MClass mclass,
@@ -691,7 +703,7 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   g.ep.split_fmt = h->gemm.split_fmt;
   const double f = 2.0 * n_rows_w * w.k;
   if (mclass == kMSurface) h->coef_t1 += f; else if (mclass == kMEncoder) h->coef_t2 += f;
-  else if (mclass == kMUnique) h->coef_u += f; else h->coef_rows += f;
+  else if (mclass == kMUnique) h->coef_u += f; else if (mclass == kMPairs) h->coef_p += f; else h->coef_rows += f;
   ZETT_TRY(h->gemm.launch(g, stream));
   if (debug_enabled()) {
     char name[64];
@@ -726,7 +738,7 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
   const int n_layers = h->cfg.hn_n_layers;
   int* counts = w.counts_all + (h->passes % kMaxPassSlots) * kCntSlots;
   const int fmt = h->gemm.split_fmt;
-  h->coef_t1 = h->coef_t2 = h->coef_rows = h->coef_u = 0;
+  h->coef_t1 = h->coef_t2 = h->coef_rows = h->coef_u = h->coef_p = 0;
   const long long capu = w.uniq_cap;
 
   // ---- pack ------------------------------------------------------------------------------------------------------
@@ -738,6 +750,12 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
   pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_src = w.tok_src; pp.tok_pos = w.tok_pos;
   pp.tok_enc = w.tok_enc; pp.tok1_row = w.tok1_row; pp.lang_enc = w.lang_enc; pp.tok2_row = w.tok2_row; pp.tok2_valid = w.tok2_valid;
   pp.id_claim = w.id_claim; pp.id_slot = w.id_slot; pp.uniq_src = w.uniq_src; pp.tok_u = w.tok_u;
+  // the first encoder layer runs on distinct (id, position) pairs unless it is also the (pruned) last one
+  const bool pairs = h->dedup_pairs && n_layers > 1;
+  if (pairs) {
+    ZETT_CUDA(cudaMemsetAsync(w.pair_claim, 0x7F, sizeof(int) * static_cast<size_t>(capu) * L, stream));
+    pp.pair_claim = w.pair_claim; pp.pair_slot = w.pair_slot; pp.pair_u = w.pair_u; pp.pair_pos = w.pair_pos; pp.enc_pair = w.enc_pair;
+  }
   pack_rows_kernel<<<1, kPackThreads, 0, stream>>>(pp);
   ZETT_CUDA(cudaGetLastError());
   ++h->gemm.launches;
@@ -773,7 +791,8 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
     ln.a = w.F2; ln.lda = H; ln.in_index = w.tok_u; ln.vec0 = h->type0; ln.table = h->pos_table; ln.table_idx = w.tok_pos;
     ln.gamma = h->emb_ln_w; ln.beta = h->emb_ln_b; ln.eps = h->cfg.encoder_layer_norm_eps;
     ln.n_dev = counts + kCntSurface; ln.out_index = w.tok_enc;
-    ln.out_f32 = w.F3; ln.out_p0 = w.PH_a; ln.out_p1 = plane1(w.PH_a, cap2 * H, h);
+    ln.out_f32 = w.F3;
+    if (!pairs) { ln.out_p0 = w.PH_a; ln.out_p1 = plane1(w.PH_a, cap2 * H, h); }  // else: operand rows per distinct pair below
     if (single_layer) {
       ln.tok_row = w.tok1_row; ln.row_start = w.row_start1;
       ln.c_f32 = w.CX0; ln.c_p0 = w.CPX0; ln.c_p1 = plane1(w.CPX0, capr * H, h);
@@ -785,8 +804,26 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
       ll.table = h->pos_table; ll.table_idx = nullptr; ll.table_const = L;
       ll.gamma = h->emb_ln_w; ll.beta = h->emb_ln_b; ll.eps = h->cfg.encoder_layer_norm_eps;
       ll.n_host = rows; ll.out_index = w.lang_enc;
-      ll.out_f32 = w.F3; ll.out_p0 = w.PH_a; ll.out_p1 = plane1(w.PH_a, cap2 * H, h);
+      ll.out_f32 = w.F3;
+      if (!pairs) { ll.out_p0 = w.PH_a; ll.out_p1 = plane1(w.PH_a, cap2 * H, h); }
       ZETT_TRY(launch_ln(h, ll, rows, stream));
+    }
+    if (pairs) {  // the same LayerNorm once per distinct (id, position) pair -> operand planes of the layer-0 QKV GEMM
+      LnParams lp{};
+      lp.a = w.F2; lp.lda = H; lp.in_index = w.pair_u; lp.vec0 = h->type0; lp.table = h->pos_table; lp.table_idx = w.pair_pos;
+      lp.gamma = h->emb_ln_w; lp.beta = h->emb_ln_b; lp.eps = h->cfg.encoder_layer_norm_eps;
+      lp.n_dev = counts + kCntPairs;
+      lp.out_p0 = w.PH_a; lp.out_p1 = plane1(w.PH_a, cap2 * H, h);
+      ZETT_TRY(launch_ln(h, lp, cap1 + 1, stream));
+      if (lang) {  // pair 0 = the lang-id position (after the launch above, which wrote a placeholder there)
+        LnParams ll{};
+        ll.a = h->lang_pre + static_cast<long long>(lang_index) * H; ll.lda = 0; ll.vec0 = h->type0;
+        ll.table = h->pos_table; ll.table_idx = nullptr; ll.table_const = L;
+        ll.gamma = h->emb_ln_w; ll.beta = h->emb_ln_b; ll.eps = h->cfg.encoder_layer_norm_eps;
+        ll.n_host = 1;
+        ll.out_p0 = w.PH_a; ll.out_p1 = plane1(w.PH_a, cap2 * H, h);
+        ZETT_TRY(launch_ln(h, ll, 1, stream));
+      }
     }
   }
 
@@ -796,9 +833,11 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
     const EncoderLayer& ly = h->layers[l];
     const bool last = l == n_layers - 1;
     if (!last) {
-      ZETT_TRY(run_linear(h, ly.qkv, 0, 3 * H, w.PH_a, cap2, kMEncoder, 0, counts, kActNone, w.F4, 3 * H, nullptr, 0,
-                          nullptr, nullptr, stream));
+      const bool on_pairs = pairs && l == 0;
+      ZETT_TRY(run_linear(h, ly.qkv, 0, 3 * H, w.PH_a, cap2, on_pairs ? kMPairs : kMEncoder, 0, counts, kActNone, w.F4, 3 * H,
+                          nullptr, 0, nullptr, nullptr, stream));
       AttnParams ap{};
+      ap.qkv_index = on_pairs ? w.enc_pair : nullptr;
       ap.q = w.F4; ap.ldq = 3 * H; ap.k = w.F4 + H; ap.ldk = 3 * H; ap.v = w.F4 + 2 * H; ap.ldv = 3 * H;
       ap.row_start = w.row_start2; ap.valid = w.tok2_valid; ap.n_rows = rows; ap.n_heads = h->heads; ap.dh = h->dh;
       ap.scale = scale; ap.row0_only = 0; ap.out_p0 = w.PH_b; ap.out_p1 = plane1(w.PH_b, cap2 * H, h); ap.ld_out = H;
@@ -943,6 +982,7 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
   h->gemm.set_precision(terms);
   h->gemm.read_env();
+  if (const char* e = getenv("ZETT_DEDUP_PAIRS")) h->dedup_pairs = atoi(e) != 0;
   *out = h;
   return ZETT_OK;
 }
@@ -1107,7 +1147,7 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
     const long long n_pass = std::min<long long>(-h->stats.packed_positions, kMaxPassSlots);
     std::vector<int> host(static_cast<size_t>(kMaxPassSlots) * kCntSlots);
     ZETT_CUDA(cudaMemcpy(host.data(), h->ws.counts_all, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
-    long long t1 = 0, t2 = 0, rows = 0, uq = 0;
+    long long t1 = 0, t2 = 0, rows = 0, uq = 0, pq = 0;
     int bad = 0;
     for (long long i = 0; i < n_pass; ++i) {
       const long long slot = ((h->passes - 1 - i) % kMaxPassSlots + kMaxPassSlots) % kMaxPassSlots;
@@ -1115,12 +1155,14 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
       t2 += host[slot * kCntSlots + kCntEncoder];
       rows += host[slot * kCntSlots + kCntRows];
       uq += host[slot * kCntSlots + kCntUnique];
+      pq += host[slot * kCntSlots + kCntPairs];
       bad |= host[slot * kCntSlots + kCntBadId];
     }
     h->stats.packed_positions = t1;
     h->stats.encoder_positions = t2;
-    h->stats.flops_executed = h->coef_t1 * t1 + h->coef_t2 * t2 + h->coef_rows * rows + h->coef_u * uq;
+    h->stats.flops_executed = h->coef_t1 * t1 + h->coef_t2 * t2 + h->coef_rows * rows + h->coef_u * uq + h->coef_p * pq;
     h->stats.distinct_ids = uq;
+    h->stats.distinct_pairs = pq;
     if (bad)
       return fail(ZETT_ERR_INDEX, "surface-form id outside [0, original_vocab_size + max(hn_n_extra_tokens, 1))");
   }

@@ -25,7 +25,7 @@ constexpr int kPackThreads = 1024;
 constexpr int kMaxSurfaceLen = 32;
 
 // counts[] slots
-enum : int { kCntSurface = 0, kCntEncoder = 1, kCntBadId = 2, kCntRows = 3, kCntUnique = 4, kCntSlots = 8 };
+enum : int { kCntSurface = 0, kCntEncoder = 1, kCntBadId = 2, kCntRows = 3, kCntUnique = 4, kCntPairs = 5, kCntSlots = 8 };
 
 struct PackParams {
   const int32_t* ids;    // [n_rows, L]
@@ -48,6 +48,14 @@ struct PackParams {
   int* id_slot;                // [v0 + n_fallback] scratch: index of the id among the distinct ids
   int* uniq_src;               // [U]   tok_src code of each distinct id, in order of first occurrence
   int* tok_u;                  // [T1]  index into the distinct ids
+  // de-duplication of the first encoder layer's input: LayerNorm(projection[id] + type + position[pos]) and the
+  // query/key/value rows computed from it depend on the (id, position) pair only, so they are evaluated once per
+  // DISTINCT pair of the pass (nullable: pair_claim == nullptr switches this off)
+  int* pair_claim;             // [U_cap * L] scratch, preset to INT_MAX-like: lowest position holding the pair
+  int* pair_slot;              // [U_cap * L] scratch: index of the pair among the distinct pairs
+  int* pair_u;                 // [P]   distinct-id index of each distinct pair   (slot 0 = the lang-id position when lang_slot)
+  int* pair_pos;               // [P]   position id of each distinct pair
+  int* enc_pair;               // [T2]  distinct-pair index of every encoder position
 };
 
 __device__ __forceinline__ uint32_t kept_mask(const int32_t* row, int L, int pad_id, int lang_slot, uint32_t& nonpad) {
@@ -167,6 +175,46 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_rows_kernel(const PackPa
   }
   __syncthreads();
   for (int t = t_begin; t < t_end; ++t) p.tok_u[t] = __ldcg(&p.id_slot[p.tok_src[t]]);
+  if (!p.pair_claim) return;
+  // ---- distinct (id, position) pairs: same owner scheme over the key  distinct-id index * L + position ----------
+  for (int t = t_begin; t < t_end; ++t) atomicMin(&p.pair_claim[p.tok_u[t] * p.L + p.tok_pos[t]], t);
+  __syncthreads();
+  int powners = 0;
+  for (int t = t_begin; t < t_end; ++t) powners += (__ldcg(&p.pair_claim[p.tok_u[t] * p.L + p.tok_pos[t]]) == t) ? 1 : 0;
+  int pincl = powners;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, pincl, o);
+    if (lane >= o) pincl += v;
+  }
+  if (lane == 31) warp_sums[warp] = pincl;
+  __syncthreads();
+  const int pair_base = p.lang_slot ? 1 : 0;  // slot 0 is the lang-id position, identical for every row
+  if (warp == 0) {
+    const int w = warp_sums[lane];
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_sums2[lane] = wi - w;
+    if (lane == 31) p.counts[kCntPairs] = wi + pair_base;
+    if (lane == 0 && pair_base) { p.pair_u[0] = 0; p.pair_pos[0] = 0; }  // placeholder row, overwritten by the lang-id LayerNorm
+  }
+  __syncthreads();
+  int pu = pair_base + warp_sums2[warp] + pincl - powners;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int key = p.tok_u[t] * p.L + p.tok_pos[t];
+    if (__ldcg(&p.pair_claim[key]) == t) {
+      p.pair_slot[key] = pu;
+      p.pair_u[pu] = p.tok_u[t];
+      p.pair_pos[pu] = p.tok_pos[t];
+      ++pu;
+    }
+  }
+  __syncthreads();
+  for (int t = t_begin; t < t_end; ++t) p.enc_pair[p.tok_enc[t]] = __ldcg(&p.pair_slot[p.tok_u[t] * p.L + p.tok_pos[t]]);
+  if (p.lang_slot)
+    for (int r = r0; r < r1; ++r) p.enc_pair[p.lang_enc[r]] = 0;
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -406,6 +454,7 @@ struct AttnParams {
   const float* v; long long ldv;
   const int* row_start;          // encoder packing [n_rows + 1]
   const unsigned char* valid;    // [T2]
+  const int* qkv_index;          // nullable [T2]: row of q / k / v holding encoder position t (distinct-pair rows)
   int n_rows, n_heads, dh;
   float scale;
   int row0_only;
@@ -432,7 +481,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   // K and V are streamed per query (L1-resident re-reads); keeping them in registers was measured slower: the kernel is
   // latency-bound and the register footprint cost more occupancy than the re-reads cost bandwidth
   for (int i = 0; i < n_q; ++i) {
-    const long long qi = p.row0_only ? r : (t0 + i);
+    const long long qi = p.row0_only ? r : (p.qkv_index ? __ldg(p.qkv_index + t0 + i) : (t0 + i));
     float qv[DPL];
 #pragma unroll
     for (int d = 0; d < DPL; ++d) qv[d] = __ldg(p.q + qi * p.ldq + hoff + 32 * d);
@@ -443,7 +492,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
       if (any_valid && !((valid_mask >> j) & 1u)) continue;  // masked key: weight exactly 0
       float s = 0.f;
       if (any_valid) {
-        const float* kj = p.k + static_cast<long long>(t0 + j) * p.ldk + hoff;
+        const float* kj = p.k + static_cast<long long>(p.qkv_index ? __ldg(p.qkv_index + t0 + j) : (t0 + j)) * p.ldk + hoff;
 #pragma unroll
         for (int d = 0; d < DPL; ++d) s += qv[d] * __ldg(kj + 32 * d);
 #pragma unroll
@@ -454,7 +503,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
       const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
       const float w = expf(s - m_new);
       l = l * corr + w;
-      const float* vj = p.v + static_cast<long long>(t0 + j) * p.ldv + hoff;
+      const float* vj = p.v + static_cast<long long>(p.qkv_index ? __ldg(p.qkv_index + t0 + j) : (t0 + j)) * p.ldv + hoff;
 #pragma unroll
       for (int d = 0; d < DPL; ++d) acc[d] = acc[d] * corr + w * __ldg(vj + 32 * d);
       m = m_new;
