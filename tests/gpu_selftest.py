@@ -151,20 +151,46 @@ def run_sustained(mnk_list, seconds=1.5):
         a = torch.randn(m, k, device=dev)
         w = torch.randn(n, k, device=dev) / k ** 0.5
         out = torch.empty((m, n), device=dev)
-        variants = [(impl, terms, mask) for impl in (2, 4) for (terms, mask) in ((3, 7), (3, 1), (2, 7), (2, 1), (2, 4), (1, 7))]
-        for (impl, terms, mask) in variants:
+        # (label, impl, terms, MMA mask, store the output?, environment)
+        W_LAST, A_FIRST, STREAM = {"ZETT_L2_HINT_W": "3"}, {"ZETT_L2_HINT_A": "1"}, {"ZETT_STREAM_OUT": "1"}
+        variants = [
+            ("bf16x3", 2, 3, 7, True, {}),
+            ("bf16x3 W=evict_last", 2, 3, 7, True, W_LAST),
+            ("bf16x3 W=evict_last, streaming stores", 2, 3, 7, True, {**W_LAST, **STREAM}),
+            ("bf16x3 W=evict_last, A=evict_first, streaming stores", 2, 3, 7, True, {**W_LAST, **A_FIRST, **STREAM}),
+            ("bf16x3 streaming stores", 2, 3, 7, True, STREAM),
+            ("bf16x3 no store", 2, 3, 7, False, {}),
+            ("bf16x3 no MMA", 2, 3, 0, True, {}),
+            ("bf16x3 no MMA, no store (loads only)", 2, 3, 0, False, {}),
+            ("bf16x3 main term only", 2, 3, 1, True, {}),
+            ("f16+2xe5m2", 2, 2, 7, True, {}),
+            ("f16+2xe5m2 W=evict_last, streaming stores", 2, 2, 7, True, {**W_LAST, **STREAM}),
+            ("f16+2xe5m2 main term only", 2, 2, 1, True, {}),
+            ("f16+2xe5m2 fp8 terms only", 2, 2, 4, True, {}),
+            ("f16+2xe5m2 pairs of pairs", 4, 2, 7, True, {}),
+            ("bf16 single pass", 2, 1, 7, True, {}),
+            ("bf16 single pass no store", 2, 1, 7, False, {}),
+        ]
+        for (label, impl, terms, mask, store, env) in variants:
             os.environ["ZETT_MMA_MASK"] = str(mask)
+            for kk in ("ZETT_L2_HINT_W", "ZETT_L2_HINT_A", "ZETT_STREAM_OUT"):
+                os.environ.pop(kk, None)
+            os.environ.update(env)
+            act = 0 if store else 0x100
             ms = ctypes.c_float(0)
-            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, 0, impl, terms, 2,
+            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, act, impl, terms, 2,
                                          ctypes.byref(ms), None))
             iters = max(4, int(seconds * 1e3 / max(ms.value / 2, 1e-3)))
             ps = PowerSampler()
-            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, 0, impl, terms, iters,
+            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, act, impl, terms, iters,
                                          ctypes.byref(ms), None))
             st = ps.stop()
             t = ms.value / iters
-            print(json.dumps(dict(kind="sustained", m=m, n=n, k=k, impl=impl, terms=terms, mma_mask=mask, iters=iters,
-                                  ms=round(t, 4), tflops_once=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), **st)), flush=True)
+            print(json.dumps(dict(kind="sustained", label=label, m=m, n=n, k=k, impl=impl, terms=terms, mma_mask=mask,
+                                  store=store, iters=iters, ms=round(t, 4),
+                                  tflops_once=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), **st)), flush=True)
+        for kk in ("ZETT_L2_HINT_W", "ZETT_L2_HINT_A", "ZETT_STREAM_OUT"):
+            os.environ.pop(kk, None)
         os.environ.pop("ZETT_MMA_MASK", None)
         ab, wb = a.bfloat16(), w.bfloat16()
         ob = torch.empty((m, n), device=dev, dtype=torch.bfloat16)

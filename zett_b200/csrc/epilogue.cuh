@@ -18,7 +18,10 @@ enum Act : int { kActNone = 0, kActGeluTanh = 1, kActGeluErf = 2 };
 //                           weights    : q0 = e5m2(2^-6 w),        q1 = e5m2(2^6 (w - p0))
 //                         A.W ~= A0 W0 (f16 MMA) + Aq0 Wq0 + Aq1 Wq1 (two f8f6f4 MMAs, half the cost each);
 //                         the 2^+-6 factors cancel inside each product and keep both fp8 operands in e5m2's normal range.
-//   The two fp8 planes live where plane 1 lives (same 2 bytes per element): q0 = (uint8*)p1, q1 = q0 + (p1 - p0).
+//   The two fp8 planes live where plane 1 lives (same 2 bytes per element), INTERLEAVED per block of 64 K-elements so
+//   that one 128-byte line holds q0[64] | q1[64] of a (row, k-block): the TMA boxes of the fp8 planes then fetch whole
+//   lines with the 128-byte swizzle, like the 16-bit planes (two 64-byte half-line planes cost 1.5x the L2 requests).
+//   Byte address of element offset `off` (row * K + k, K a multiple of 64):  q0 at 2 * off - (off & 63), q1 64 further.
 enum SplitFmt : int { kFmtBf16 = 0, kFmtFp16 = 1, kFmtF16F8 = 2 };
 constexpr float kF8Up = 64.0f, kF8Down = 0.015625f;
 
@@ -35,6 +38,7 @@ struct EpilogueParams {
   uint16_t* out_p1;
   long long ld_split;
   int split_fmt;
+  int stream_f32;           // 1: fp32 output stored with the streaming (evict-first) hint, it is larger than L2
 };
 
 // F.gelu(x, approximate="tanh")  (ProjectorBlock, hf_hypernet/modeling_hypernet.py:36-39)
@@ -67,6 +71,9 @@ __device__ __forceinline__ float e5m2_to_float(uint8_t v) {
   return __half2float(__half(hr));
 }
 
+// byte offset of q0 of the element at offset `off` inside the interleaved fp8 region (q1 = +64)
+__device__ __forceinline__ long long f8_offset(long long off) { return 2 * off - (off & 63); }
+
 __device__ __forceinline__ uint32_t pack4_u8(const uint8_t* b) {
   return uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16) | (uint32_t(b[3]) << 24);
 }
@@ -81,10 +88,9 @@ __device__ __forceinline__ void store_operand4(uint16_t* p0, uint16_t* p1, long 
     uint2 pa;
     pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
     *reinterpret_cast<uint2*>(p0 + off) = pa;
-    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1);
-    uint8_t* q1 = q0 + (p1 - p0);
-    *reinterpret_cast<uint32_t*>(q0 + off) = pack4_u8(b);
-    *reinterpret_cast<uint32_t*>(q1 + off) = pack4_u8(c);
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1) + f8_offset(off);
+    *reinterpret_cast<uint32_t*>(q0) = pack4_u8(b);
+    *reinterpret_cast<uint32_t*>(q0 + 64) = pack4_u8(c);
   } else {
     uint16_t a[4], b[4];
 #pragma unroll
@@ -118,10 +124,9 @@ __device__ __forceinline__ void store_operand8(uint16_t* p0, uint16_t* p1, long 
     pa.x = a[0] | (uint32_t(a[1]) << 16); pa.y = a[2] | (uint32_t(a[3]) << 16);
     pa.z = a[4] | (uint32_t(a[5]) << 16); pa.w = a[6] | (uint32_t(a[7]) << 16);
     *reinterpret_cast<uint4*>(p0 + off) = pa;
-    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1);
-    uint8_t* q1 = q0 + (p1 - p0);
-    *reinterpret_cast<uint2*>(q0 + off) = make_uint2(pack4_u8(b), pack4_u8(b + 4));
-    *reinterpret_cast<uint2*>(q1 + off) = make_uint2(pack4_u8(c), pack4_u8(c + 4));
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1) + f8_offset(off);
+    *reinterpret_cast<uint2*>(q0) = make_uint2(pack4_u8(b), pack4_u8(b + 4));
+    *reinterpret_cast<uint2*>(q0 + 64) = make_uint2(pack4_u8(c), pack4_u8(c + 4));
   } else {
     store_operand4(p0, p1, off, y, fmt, is_weight);
     store_operand4(p0, p1, off + 4, y + 4, fmt, is_weight);
@@ -135,9 +140,9 @@ __device__ __forceinline__ void store_operand1(uint16_t* p0, uint16_t* p1, long 
     uint8_t b, c;
     split_f16f8(y, false, a, b, c);
     p0[off] = a;
-    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1);
-    q0[off] = b;
-    (q0 + (p1 - p0))[off] = c;
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(p1) + f8_offset(off);
+    q0[0] = b;
+    q0[64] = c;
   } else if (fmt == kFmtBf16) {
     const __nv_bfloat16 h = __float2bfloat16_rn(y);
     p0[off] = __bfloat16_as_ushort(h);
@@ -209,7 +214,10 @@ __device__ __forceinline__ void epilogue_full32(const EpilogueParams& ep, int ro
   if (ep.out_f32) {
     float4* o = reinterpret_cast<float4*>(ep.out_f32 + static_cast<long long>(row) * ep.ld_out + col0);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 8; ++q) {
+      const float4 y = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (ep.stream_f32) __stcs(o + q, y); else o[q] = y;
+    }
   }
   if (ep.out_p0) {
     const long long off = static_cast<long long>(row) * ep.ld_split + col0;

@@ -5,8 +5,8 @@
 //    A0*B0 + A1*B0 + A0*B1 into the SAME TMEM accumulator (n_terms == 3; n_terms == 1 issues A0*B0 only), which restores
 //    ~fp32 operand precision (the 1e-3 parity budget rules out single-pass bf16); or fp16 + two e5m2
 //    correction planes (f8): one kind::f16 MMA + two kind::f8f6f4 MMAs per k-step.
-//  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}; 128-byte swizzle for 16-bit rows of BLOCK_K = 64, 64-byte
-//    for the fp8 planes), warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / residual /
+//  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}; 128-byte swizzle: 16-bit rows of BLOCK_K = 64, or the two
+//    fp8 planes of a k-block interleaved in one line), warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / residual /
 //    column affine -> fp32 and/or operand planes for the next GEMM).
 //  * accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the main loop of
 //    tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
@@ -46,11 +46,12 @@ struct GemmShape {
   int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
   int f8;              // 1: operand format kFmtF16F8 -- one fp16 plane + two e5m2 correction planes (epilogue.cuh)
   int mma_mask;        // diagnostic (ZETT_MMA_MASK, default 7): bit 0 main term, bit 1 16-bit correction terms, bit 2 fp8 terms
+  uint64_t hint_a, hint_b;   // L2 eviction policies of the A / W loads (ptx.cuh)
   uint32_t idesc;      // tcgen05 instruction descriptor (kind::f16)
   uint32_t idesc8;     // tcgen05 instruction descriptor (kind::f8f6f4), f8 only
   int num_stages;
   uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;   // 16-bit planes: 128-byte rows
-  uint32_t a8_plane_bytes, b8_plane_bytes;              // fp8 planes: 64-byte rows
+  uint32_t a8_bytes, b8_bytes;                          // interleaved fp8 planes: 128-byte rows (q0[64] | q1[64])
 };
 
 struct TileCoord { int m_blk, n_blk; };
@@ -150,25 +151,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t a_dst = smem_base + stage * s.stage_bytes;
           const uint32_t b_dst = a_dst + s.n_planes * s.a_plane_bytes;
           const uint32_t a8_dst = b_dst + s.n_planes * s.b_plane_bytes;
-          const uint32_t b8_dst = a8_dst + 2u * s.a8_plane_bytes;
+          const uint32_t b8_dst = a8_dst + s.a8_bytes;
           if constexpr (CG == 1) {
             mbar_expect_tx(full_bar(stage), s.stage_bytes);
-            tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0);
-            tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0);
+            tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0, s.hint_a);
+            tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0, s.hint_b);
             if (s.f8) {
-              tma_load_3d(&tmap_a8, full_bar(stage), a8_dst, kb * s.block_k, row_a, 0);
-              tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
+              tma_load_3d(&tmap_a8, full_bar(stage), a8_dst, kb * 128, row_a, 0, s.hint_a);
+              tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * 128, row_b, 0, s.hint_b);
             }
           } else {
             // only the leader arrives (expecting the bytes landing in both CTAs of its pair); the other copies credit
             // that barrier directly, so no other loop carries a cluster-scope operation.  Bytes may land before the
             // leader's expect_tx: the phase cannot complete until that arrive, and the transaction count is signed.
             if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
-            tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0);
-            if (s.f8) tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * s.block_k, row_a, 0);
+            tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0, s.hint_a);
+            if (s.f8) tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * 128, row_a, 0, s.hint_a);
             if constexpr (CP == 1) {
-              tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0);
-              if (s.f8) tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * s.block_k, row_b, 0);
+              tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0, s.hint_b);
+              if (s.f8) tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * 128, row_b, 0, s.hint_b);
             } else {
               // this CTA fetches rows [pair * load_n / 2, +load_n / 2) of its share, plane by plane, for itself and for the
               // CTA of equal pair rank in the other pair; the other half arrives from there.  Each copy credits the full
@@ -178,12 +179,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               const uint16_t mask = static_cast<uint16_t>(0x5u << cta_rank);
               const uint32_t off16 = pair * static_cast<uint32_t>(share) * static_cast<uint32_t>(s.block_k) * 2u;
               for (int pl = 0; pl < s.n_planes; ++pl)
-                tma_load_3d_2sm_mc(&tmap_b, full_bar(stage), b_dst + pl * s.b_plane_bytes + off16, kb * s.block_k, row_s, pl, mask);
-              if (s.f8) {
-                const uint32_t off8 = off16 >> 1;
-                for (int pl = 0; pl < 2; ++pl)
-                  tma_load_3d_2sm_mc(&tmap_b8, full_bar(stage), b8_dst + pl * s.b8_plane_bytes + off8, kb * s.block_k, row_s, pl, mask);
-              }
+                tma_load_3d_2sm_mc(&tmap_b, full_bar(stage), b_dst + pl * s.b_plane_bytes + off16, kb * s.block_k, row_s, pl, mask, s.hint_b);
+              if (s.f8)
+                tma_load_3d_2sm_mc(&tmap_b8, full_bar(stage), b8_dst + pair * static_cast<uint32_t>(share) * 128u, kb * 128, row_s, 0, mask, s.hint_b);
             }
           }
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
@@ -224,13 +222,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (s.f8 && (s.mma_mask & 4)) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
             const uint32_t a8 = b0 + s.n_planes * s.b_plane_bytes;
-            const uint32_t b8 = a8 + 2u * s.a8_plane_bytes;
+            const uint64_t dqa = umma_desc_kmajor(a8, 128u), dqb = umma_desc_kmajor(a8 + s.a8_bytes, 128u);
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl) {
-              const uint64_t dqa = umma_desc_kmajor(a8 + pl * s.a8_plane_bytes, static_cast<uint32_t>(s.block_k));
-              const uint64_t dqb = umma_desc_kmajor(b8 + pl * s.b8_plane_bytes, static_cast<uint32_t>(s.block_k));
-              for (int kk = 0; kk < s.block_k / 32; ++kk) umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, 1u);
-            }
+            for (int kk = 0; kk < 4; ++kk)  // bytes [0, 64) of a row are q0 of the k-block, [64, 128) are q1
+              umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, (s.mma_mask & 1) | kb | kk);
           }
           umma_commit<CG>(empty_bar(stage), kAllMask);                      // frees the stage in every CTA of the cluster
           if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc), kPairMask);  // accumulator complete (this pair)

@@ -91,22 +91,21 @@ int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long
   return ZETT_OK;
 }
 
-// 3-D map {K, rows, 2} over the two e5m2 correction planes, box {64, box_rows, 2}, 64-byte swizzle
-int make_plane8_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long k, long long plane_stride_bytes,
-                     int box_rows, int box_planes, int block_k) {
+// map over the interleaved e5m2 correction planes (epilogue.cuh): rows of 2 K bytes, box {128 bytes, box_rows}, 128-byte swizzle
+int make_plane8_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long k, int box_rows) {
   EncodeTiledFn enc;
   ZETT_TRY(get_encode_fn(&enc));
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), 2};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(plane_stride_bytes)};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_planes)};
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(2 * k), static_cast<cuuint64_t>(rows), 1};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(2 * k), static_cast<cuuint64_t>(2 * k) * static_cast<cuuint64_t>(rows)};
+  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(block_k), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (fp8 planes) failed (%d): rows=%lld k=%lld plane_stride=%lld box_rows=%d",
-             static_cast<int>(r), rows, k, plane_stride_bytes, box_rows);
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (fp8 planes) failed (%d): rows=%lld k=%lld box_rows=%d", static_cast<int>(r), rows, k,
+             box_rows);
     return fail(ZETT_ERR_CUDA, buf);
   }
   return ZETT_OK;
@@ -167,7 +166,7 @@ struct GemmArgs {
   long long a_plane_stride = 0;    // elements between plane 0 and plane 1
   const uint16_t* w = nullptr;     // plane 0 of W, [n, k]
   long long w_plane_stride = 0;
-  const uint8_t* a_q = nullptr;    // kFmtF16F8: first fp8 plane of A / W (second one plane_stride bytes further)
+  const uint8_t* a_q = nullptr;    // kFmtF16F8: interleaved fp8 planes of A / W, rows of 2 K bytes
   const uint8_t* w_q = nullptr;
   int n = 0, k = 0;
   int m_host = 0;
@@ -186,6 +185,14 @@ struct GemmEngine {
     if (const char* e = getenv("ZETT_RASTER_CHUNK_MB")) raster_chunk_bytes = std::max(1ll, atoll(e)) << 20;
     if (const char* e = getenv("ZETT_RASTER_GROUP_M")) raster_group_m = std::max(1, atoi(e));
     if (const char* e = getenv("ZETT_BLOCK_K")) block_k = atoi(e) == 32 ? 32 : 64;
+    auto hint = [](const char* e, uint64_t dflt) -> uint64_t {
+      if (!e) return dflt;
+      const int v = atoi(e);
+      return v == 1 ? kL2EvictFirst : (v == 3 ? kL2EvictLast : kL2EvictNormal);
+    };
+    hint_a = hint(getenv("ZETT_L2_HINT_A"), hint_a);   // 1 evict_first, 2 normal, 3 evict_last
+    hint_b = hint(getenv("ZETT_L2_HINT_W"), hint_b);
+    if (const char* e = getenv("ZETT_STREAM_OUT")) stream_out = atoi(e) != 0;
     if (const char* e = getenv("ZETT_MMA_MASK")) mma_mask = atoi(e) & 7;  // energy / throughput probes only: results are wrong
   }
   void set_precision(int terms) {
@@ -198,6 +205,8 @@ struct GemmEngine {
   int raster_group_m = 4;
   int block_k = 64;        // K per pipeline stage (64 or 32)
   int mma_mask = 7;        // diagnostic: which product terms are issued (gemm_tcgen05.cuh)
+  uint64_t hint_a = kL2EvictNormal, hint_b = kL2EvictNormal;  // L2 eviction policies of the operand loads
+  bool stream_out = false; // fp32 outputs stored with the streaming hint
   bool timing = false;
   std::vector<cudaEvent_t> events;
   size_t events_used = 0;
@@ -237,13 +246,12 @@ struct GemmEngine {
     *out = &it->second;
     return ZETT_OK;
   }
-  int tmap8(const uint8_t* base, long long rows, long long k, long long plane_stride, int box_rows, int box_planes,
-            const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k, 8 + 16 * box_planes);
+  int tmap8(const uint8_t* base, long long rows, long long k, int box_rows, const CUtensorMap** out) {
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, 0ll, box_rows, 8);
     auto it = tmaps.find(key);
     if (it == tmaps.end()) {
       CUtensorMap m;
-      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, plane_stride, box_rows, box_planes, block_k));
+      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, box_rows));
       it = tmaps.emplace(key, m).first;
     }
     *out = &it->second;
@@ -256,22 +264,26 @@ struct GemmEngine {
   }
 
   int launch(const GemmArgs& g, cudaStream_t stream) {
+    EpilogueParams ep = g.ep;
+    ep.stream_f32 = stream_out ? 1 : 0;
     if (g.k % 8 != 0) return fail(ZETT_ERR_INVALID, "GEMM K must be a multiple of 8");
     ++launches;
     const int n_planes = n_terms == 3 ? 2 : 1;
     const bool f8 = n_terms == 2;
     if (f8 && (!g.a_q || !g.w_q)) return fail(ZETT_ERR_INVALID, "fp8 planes missing");
+    if (f8 && g.k % 64 != 0) return fail(ZETT_ERR_INVALID, "split_terms = 2 needs every GEMM K (n_embd, hidden, intermediate sizes) to be a multiple of 64");
+    if (f8) block_k = 64;  // the fp8 planes are interleaved per 64 K-elements
     if (impl == 3) {
       SimtGemmParams s{};
       s.a0 = g.a; s.a1 = n_planes == 2 ? g.a + g.a_plane_stride : nullptr;
       s.w0 = g.w; s.w1 = n_planes == 2 ? g.w + g.w_plane_stride : nullptr;
-      s.aq = f8 ? g.a_q : nullptr; s.aq_stride = g.a_plane_stride;
-      s.wq = f8 ? g.w_q : nullptr; s.wq_stride = g.w_plane_stride;
+      s.aq = f8 ? g.a_q : nullptr;
+      s.wq = f8 ? g.w_q : nullptr;
       s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k; s.split_fmt = split_fmt;
       dim3 grid((g.n + 31) / 32, (g.m_host + 127) / 128);
       if (grid.y == 0 || grid.x == 0) return ZETT_OK;
       ZETT_TRY(time_mark(stream));
-      gemm_simt_kernel<<<grid, 128, 0, stream>>>(s, g.ep);
+      gemm_simt_kernel<<<grid, 128, 0, stream>>>(s, ep);
       ZETT_CUDA(cudaGetLastError());
       ZETT_TRY(time_mark(stream));
       return ZETT_OK;
@@ -282,13 +294,14 @@ struct GemmEngine {
     s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
     s.block_n = pick_block_n(g.n);
     s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0; s.mma_mask = mma_mask;
+    s.hint_a = hint_a; s.hint_b = hint_b;
     const int load_n = s.block_n / cg;
     s.block_k = block_k;
     s.a_plane_bytes = kBlockM * block_k * 2;
     s.b_plane_bytes = static_cast<uint32_t>(load_n) * block_k * 2;
-    s.a8_plane_bytes = f8 ? kBlockM * block_k : 0;
-    s.b8_plane_bytes = f8 ? static_cast<uint32_t>(load_n) * block_k : 0;
-    s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes) + 2u * (s.a8_plane_bytes + s.b8_plane_bytes);
+    s.a8_bytes = f8 ? kBlockM * 128 : 0;
+    s.b8_bytes = f8 ? static_cast<uint32_t>(load_n) * 128 : 0;
+    s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes) + s.a8_bytes + s.b8_bytes;
     s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack) / static_cast<int>(s.stage_bytes));
     if (s.num_stages < 2) return fail(ZETT_ERR_INVALID, "GEMM tile does not fit two pipeline stages");
     // instruction descriptor (kind::f16): D fp32, A/B bf16|fp16, both K-major, N >> 3, M >> 4
@@ -302,8 +315,8 @@ struct GemmEngine {
     ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n / cp, n_planes, cp == 2 ? 1 : n_planes, &tb));
     ta8 = ta; tb8 = tb;
     if (f8) {
-      ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, g.a_plane_stride, kBlockM, 2, &ta8));
-      ZETT_TRY(tmap8(g.w_q, g.n, g.k, g.w_plane_stride, load_n / cp, cp == 2 ? 1 : 2, &tb8));
+      ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, kBlockM, &ta8));
+      ZETT_TRY(tmap8(g.w_q, g.n, g.k, load_n / cp, &tb8));
     }
     const int tile_m = kBlockM * cg * cp;
     const long long m_tiles = (g.m_host + tile_m - 1) / tile_m;
@@ -342,9 +355,9 @@ struct GemmEngine {
     const int ctas = static_cast<int>(std::min<long long>(clusters, tiles)) * cg * cp;
     cfg.gridDim = dim3(ctas);
     ZETT_TRY(time_mark(stream));
-    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 1>, *ta, *tb, *ta8, *tb8, s, g.ep));
-    else if (cp == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 1>, *ta, *tb, *ta8, *tb8, s, g.ep));
-    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 2>, *ta, *tb, *ta8, *tb8, s, g.ep));
+    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 1>, *ta, *tb, *ta8, *tb8, s, ep));
+    else if (cp == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 1>, *ta, *tb, *ta8, *tb8, s, ep));
+    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 2>, *ta, *tb, *ta8, *tb8, s, ep));
     ZETT_TRY(time_mark(stream));
     return ZETT_OK;
   }
@@ -690,7 +703,7 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   g.a = a; g.a_rows = cap; g.a_plane_stride = cap * w.k;
   g.w = w.planes + static_cast<long long>(row_off) * w.k; g.w_plane_stride = w.plane_stride();
   g.a_q = reinterpret_cast<const uint8_t*>(a + g.a_plane_stride);
-  g.w_q = reinterpret_cast<const uint8_t*>(w.planes + w.plane_stride()) + static_cast<long long>(row_off) * w.k;
+  g.w_q = reinterpret_cast<const uint8_t*>(w.planes + w.plane_stride()) + 2ll * row_off * w.k;
   g.n = n_rows_w; g.k = w.k;
   if (mclass == kMRows) { g.m_host = m_rows; g.m_dev = nullptr; }
   else { g.m_host = static_cast<int>(cap); g.m_dev = counts + count_slot(mclass); }

@@ -535,18 +535,18 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long n4, u
 struct SimtGemmParams {
   const uint16_t* a0; const uint16_t* a1;  // A planes [M, K] (a1 nullable: single term)
   const uint16_t* w0; const uint16_t* w1;  // W planes [N, K]
-  const uint8_t* aq; long long aq_stride;  // kFmtF16F8: fp8 planes q0 = aq, q1 = aq + aq_stride
-  const uint8_t* wq; long long wq_stride;
+  const uint8_t* aq;                       // kFmtF16F8: interleaved fp8 planes of A / W (epilogue.cuh: f8_offset)
+  const uint8_t* wq;
   int m_host; const int* m_dev;
   int n, k;
   int split_fmt;
 };
 
 // value of plane `pl` (0 = main, 1 / 2 = correction planes) of an operand at element offset `off`
-__device__ __forceinline__ float operand_plane(const uint16_t* p0, const uint16_t* p1, const uint8_t* q, long long q_stride,
-                                               long long off, int pl, int fmt) {
+__device__ __forceinline__ float operand_plane(const uint16_t* p0, const uint16_t* p1, const uint8_t* q, long long off, int pl,
+                                               int fmt) {
   if (pl == 0) return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(p0[off])) : __half2float(__ushort_as_half(p0[off]));
-  if (fmt == kFmtF16F8) return q ? e5m2_to_float(q[off + (pl == 2 ? q_stride : 0)]) : 0.f;
+  if (fmt == kFmtF16F8) return q ? e5m2_to_float(q[f8_offset(off) + (pl == 2 ? 64 : 0)]) : 0.f;
   if (!p1) return 0.f;
   return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(p1[off])) : __half2float(__ushort_as_half(p1[off]));
 }
@@ -569,9 +569,9 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, 
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (gr < M && k0 + c < s.k) {
         const long long off = gr * s.k + k0 + c;
-        x0 = operand_plane(s.a0, s.a1, s.aq, s.aq_stride, off, 0, s.split_fmt);
-        x1 = operand_plane(s.a0, s.a1, s.aq, s.aq_stride, off, 1, s.split_fmt);
-        x2 = f8 ? operand_plane(s.a0, s.a1, s.aq, s.aq_stride, off, 2, s.split_fmt) : x0;
+        x0 = operand_plane(s.a0, s.a1, s.aq, off, 0, s.split_fmt);
+        x1 = operand_plane(s.a0, s.a1, s.aq, off, 1, s.split_fmt);
+        x2 = f8 ? operand_plane(s.a0, s.a1, s.aq, off, 2, s.split_fmt) : x0;
       }
       As[0][r][c] = x0; As[1][r][c] = x1; As[2][r][c] = x2;
     }
@@ -581,13 +581,13 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, 
       float y0 = 0.f, y1 = 0.f, y2 = 0.f;
       if (gn < s.n && k0 + c < s.k) {
         const long long off = gn * s.k + k0 + c;
-        y0 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 0, s.split_fmt);
+        y0 = operand_plane(s.w0, s.w1, s.wq, off, 0, s.split_fmt);
         if (f8) {
-          y1 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 1, s.split_fmt);
-          y2 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 2, s.split_fmt);
+          y1 = operand_plane(s.w0, s.w1, s.wq, off, 1, s.split_fmt);
+          y2 = operand_plane(s.w0, s.w1, s.wq, off, 2, s.split_fmt);
         } else {
           y1 = s.a1 ? y0 : 0.f;
-          y2 = operand_plane(s.w0, s.w1, s.wq, s.wq_stride, off, 1, s.split_fmt);
+          y2 = operand_plane(s.w0, s.w1, s.wq, off, 1, s.split_fmt);
         }
       }
       Ws[0][r][c] = y0; Ws[1][r][c] = y1; Ws[2][r][c] = y2;

@@ -91,27 +91,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
+// L2 eviction-priority policies for the TMA loads (the encodings createpolicy.fractional.L2::evict_* produces for fraction 1.0)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+
 // 3-D tiled load global -> this CTA's smem, completion on this CTA's mbarrier
-__device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
 // 2-CTA variant: data lands in this CTA's smem, bytes are credited to the mbarrier of the pair's leader
 // (bit 24 of a shared::cluster address selects the CTA inside the pair; clearing it names CTA 0)
-__device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
 }
 // 2-CTA multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` (cluster ranks), and each
 // destination's bytes are credited to the barrier at `bar`'s offset in the leader of THAT CTA's pair
 __device__ __forceinline__ void tma_load_3d_2sm_mc(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                                   uint16_t cta_mask) {
+                                                   uint16_t cta_mask, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6}], [%2], %3;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3, %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
 }
 // 1-D bulk copy global -> smem (gather of whole embedding rows)
