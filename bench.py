@@ -11,6 +11,7 @@ execution of the path (threaded ATen restatement in oracle/) on a
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -196,6 +197,32 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def profile_of_largest_gemm(config, fmt_tag):
+    """DRAM bytes (read + write) of one launch of the largest GEMM of the step, from the committed ncu summary."""
+    if config != "mistral":
+        return None
+    for rnd in ("r1",):
+        path = os.path.join(ROOT, "profiles", "gemm_tcgen05_%s_%s_53248x12288x4096.csv" % (rnd, fmt_tag))
+        if not os.path.exists(path):
+            continue
+        vals = {}
+        with open(path) as f:
+            for row in csv.reader(f):
+                if len(row) >= 3:
+                    vals[row[0]] = (row[1], row[2])
+        try:
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "byte": 1.0, "Kbyte": 1e3}
+            rd = float(vals["dram__bytes_read.sum"][1]) * scale[vals["dram__bytes_read.sum"][0]]
+            wr = float(vals["dram__bytes_write.sum"][1]) * scale[vals["dram__bytes_write.sum"][0]]
+            act = vals.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("%", "nan"))[1]
+        except (KeyError, ValueError):
+            continue
+        return {"traffic": int(rd + wr),
+                "note": "%s: one isolated launch of the QKV GEMM of a 53248-position pass under ncu --set full; "
+                        "sm__pipe_tensor_cycles_active %s %%; traffic = its dram read + write bytes" % (os.path.relpath(path, ROOT), act)}
+    return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -220,7 +247,8 @@ def run_ours(args):
     cfg, hn, tokens = build_workload(args.config, rank, rows)
     lang = wl["lang"]
     weights = synthetic.make_weights(cfg, seed=0)
-    nat = NativeHypernet(cfg, weights, dev, gemm_impl=args.gemm_impl, split_terms=args.split_terms)  # C-ABI handle
+    nat = NativeHypernet(cfg, weights, dev, max_rows_per_pass=args.rows_per_pass, gemm_impl=args.gemm_impl,
+                         split_terms=args.split_terms)  # C-ABI handle
     del weights
     src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=100)).to(dev)
     D, separate = cfg.n_embd, bool(cfg.separate_out_embeddings)
@@ -275,11 +303,13 @@ def run_ours(args):
     gemm_ms, gemm_flops, launches = st["gemm_ms"], st["flops_executed"], st["kernel_launches"]
     ms_per_step = elapsed_ms / args.steps
     value = world * rows / (ms_per_step * 1e-3)
+    terms = int(st["split_terms"])
+    fmt = {3: ("bf16x3->f32", "bf16x3", 3.0), 2: ("f16+2xe5m2->f32", "f16f8", 2.0), 1: ("bf16->f32", "bf16", 1.0)}[terms]
 
     # ---- end to end from host token strings ("e2e") -----------------------------------------------------------------
     nat.set_timing(False)
     from zett_b200.transfer import TokenPipeline
-    pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=16384)
+    pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=args.rows_per_pass or 16384)
 
     def gather(blk):
         if world > 1:
@@ -312,12 +342,14 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3->f32" if args.split_terms != 1 else "bf16->f32", "data": "synthetic",
+        "dtype": fmt[0], "data": "synthetic",
         "config": {
             "workload": wl["workload"], "rows_per_gpu": rows, "total_rows": world * rows, "parallelism": "rows x%d" % world,
             "hn_tokenizer": wl["hn"] + " 32k synthetic", "nonpad_length_histogram": hist, "truncated": n_trunc,
             "l2": "inputs larger than L2 (weights + per-pass activations are GBs; nothing is re-read from a warm L2 by design)",
-            "gemm_impl": args.gemm_impl, "split_terms": 3 if args.split_terms != 1 else 1,
+            "gemm_impl": int(st["gemm_impl"]), "split_terms": terms, "rows_per_pass": args.rows_per_pass or 16384,
+            "distinct_ids_per_step": int(st["distinct_ids"]), "distinct_id_position_pairs_per_step": int(st["distinct_pairs"]),
+            "packed_positions_per_step": int(st["encoder_positions"]),
             "dense_gflop_per_row_reference": f_ref / 1e9,
             "executed_gflop_per_row": gemm_flops / rows / 1e9 if gemm_flops else None,
         },
@@ -328,16 +360,15 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
                      "kernel": "gemm_tcgen05_kernel", "peak_source": peaks["src"],
-                     "note": "achieved = FLOPs of the GEMMs issued in one step (each product counted once although the "
-                             "3-term split issues three MMAs) / summed CUDA-event time of those launches",
+                     "note": "achieved = FLOPs of the GEMMs issued in one step (each product counted once although the operand "
+                             "format issues several MMA terms per product) / summed CUDA-event time of those launches",
                      "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": st["gemm_launches"],
-                     "mma_issue_tflops": (achieved * (3 if args.split_terms not in (1, 2) else (1 if args.split_terms == 1 else 2)))
-                     if achieved else None,
-                     "profile": "profiles/gemm_tcgen05_r1_bf16x3_53248x12288x4096.csv: sm__pipe_tensor_cycles_active 99.7 % "
-                                "(ncu, isolated launch of the QKV GEMM); traffic = its dram read+write bytes"},
+                     "mma_issue_tflops_f16_equivalent": (achieved * fmt[2]) if achieved else None},
     }
-    if args.config == "mistral" and args.split_terms not in (1, 2):
-        line["roofline"]["traffic"] = 20147391000 + 2606192000  # bytes, one launch of the largest GEMM (profile above)
+    prof = profile_of_largest_gemm(args.config, fmt[1])
+    if prof:
+        line["roofline"]["traffic"] = prof["traffic"]
+        line["roofline"]["profile"] = prof["note"]
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.config, 1, 1, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {"value": r["value"], "unit": "rows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
@@ -358,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="mistral", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the workload's vocabulary size)")
+    ap.add_argument("--rows-per-pass", type=int, default=0, help="vocabulary rows per pass of the kernels (0 = the library default)")
     ap.add_argument("--gemm-impl", type=int, default=0)
     ap.add_argument("--split-terms", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -74,9 +74,10 @@ typedef struct zett_hn_config {
   int32_t gemm_impl;                       /* 0 = auto, 1 = tcgen05 1-CTA, 2 = tcgen05 CTA pairs (cta_group::2),
                                               3 = SIMT fp32 debug kernel (checker, never the default),
                                               4 = CTA pairs, two per cluster, W tile TMA-multicast between them     */
-  int32_t split_terms;                     /* operand precision: 0/3 = three bf16 MMA terms (A0W0 + A1W0 + A0W1),
-                                              2 = fp16 MMA + two e5m2 correction MMAs at fp8 rate, 1 = one bf16 pass
-                                              (1 misses the 1e-3 parity budget; for comparison only)               */
+  int32_t split_terms;                     /* operand precision: 2 = fp16 MMA + two e5m2 correction MMAs at fp8 rate
+                                              (sizes must be multiples of 64), 3 = three bf16 MMA terms (A0W0 + A1W0
+                                              + A0W1), 0 = auto (2 when the sizes allow it, else 3), 1 = one bf16
+                                              pass (misses the 1e-3 parity budget; for comparison only)            */
 } zett_hn_config;
 
 typedef struct zett_hn zett_hn;
@@ -128,6 +129,8 @@ typedef struct zett_hn_stats {
   int64_t distinct_ids;        /* distinct surface-form ids summed over the passes (input projection runs per id)  */
   int64_t distinct_pairs;      /* distinct (id, position) pairs summed over the passes (first encoder layer's
                                   LayerNorm and query/key/value GEMM run per pair); 0 when that is switched off    */
+  int64_t split_terms;         /* the operand format in effect (zett_hn_config.split_terms after "auto")           */
+  int64_t gemm_impl;           /* the GEMM implementation in effect (zett_hn_config.gemm_impl after "auto")         */
 } zett_hn_stats;
 int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out);
 

@@ -218,9 +218,10 @@ def test_pipelined_tokens_path_equals_one_shot(torch_cuda):
     np.testing.assert_array_equal(out[:, :cfg.n_embd].numpy(), one[0])
 
 
-@pytest.mark.parametrize("terms", [2])
-def test_fp8_correction_mode_parity(terms):
-    """split_terms = 2 (fp16 MMA + two e5m2 correction MMAs through kind::f8f6f4) meets the same 1e-3 budget."""
+@pytest.mark.parametrize("terms", [2, 3])
+def test_explicit_operand_formats_parity(terms):
+    """Both multi-term operand formats, requested explicitly, meet the 1e-3 budget: split_terms = 2 (fp16 MMA + two
+    e5m2 correction MMAs through kind::f8f6f4; the default when the sizes allow it) and 3 (three bf16 MMA terms)."""
     r, lines = run_selftest(["forward", "--impl", "2", "--terms", str(terms)])
     assert len(lines) == 6, r.stdout + r.stderr
     for ln in lines:
@@ -233,7 +234,9 @@ def test_shape_variants(torch_cuda):
     torch = torch_cuda
     from oracle import hypernet_oracle as ho
     from zett_b200 import synthetic
-    for overrides in (dict(hn_n_layers=2, hn_surface_maxlen=12), dict(hn_num_attention_heads=4), dict(hn_num_attention_heads=1)):
+    # n_embd = 72: GEMM K = 144 is not a multiple of 64, so the automatic operand format falls back to the bf16 split
+    for overrides in (dict(hn_n_layers=2, hn_surface_maxlen=12), dict(hn_num_attention_heads=4), dict(hn_num_attention_heads=1),
+                      dict(n_embd=72)):
         cfg, weights, model = _model(torch, "tiny", **overrides)
         src_np = synthetic.make_source_embeddings(cfg, seed=12)
         sf = synthetic.make_random_surface_forms(cfg, 77, seed=9)

@@ -41,7 +41,8 @@ class ZettHnStats(ctypes.Structure):
     """``zett_hn_stats`` (include/zett_b200.h)."""
     _fields_ = [("kernel_launches", c_int64), ("rows", c_int64), ("packed_positions", c_int64),
                 ("encoder_positions", c_int64), ("flops_executed", c_double), ("gemm_ms", c_double),
-                ("gemm_launches", c_int64), ("distinct_ids", c_int64), ("distinct_pairs", c_int64)]
+                ("gemm_launches", c_int64), ("distinct_ids", c_int64), ("distinct_pairs", c_int64),
+                ("split_terms", c_int64), ("gemm_impl", c_int64)]
 
 
 def needs_build() -> bool:

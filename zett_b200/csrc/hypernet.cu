@@ -993,6 +993,9 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   if (h->gemm.impl < 1 || h->gemm.impl > 4) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..4"); }
   int terms = cfg->split_terms;
   if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
+  // auto: fp16 + two e5m2 correction planes (fewest tensor-pipe cycles inside the 1e-3 budget) when every GEMM K is a
+  // multiple of 64 (its fp8 planes are interleaved per 64 K-elements), else the three-term bf16 split
+  if (terms == 0) terms = (h->E % 64 == 0 && H % 64 == 0 && I % 64 == 0) ? 2 : 3;
   h->gemm.set_precision(terms);
   h->gemm.read_env();
   if (const char* e = getenv("ZETT_DEDUP_PAIRS")) h->dedup_pairs = atoi(e) != 0;
@@ -1184,6 +1187,8 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
 
 int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out) {
   if (!h || !out) return fail(ZETT_ERR_INVALID, "null argument");
+  h->stats.split_terms = h->gemm.n_terms;
+  h->stats.gemm_impl = h->gemm.impl;
   *out = h->stats;
   return ZETT_OK;
 }
