@@ -73,7 +73,8 @@ typedef struct zett_hn_config {
   int32_t max_rows_per_pass;               /* rows handled by one pass of the kernels (0 -> 16384, transfer.py:44) */
   int32_t gemm_impl;                       /* 0 = auto, 1 = tcgen05 1-CTA, 2 = tcgen05 CTA pairs (cta_group::2),
                                               3 = SIMT fp32 debug kernel (checker, never the default),
-                                              4 = CTA pairs, two per cluster, W tile TMA-multicast between them     */
+                                              4 = CTA pairs, two per cluster, W tile TMA-multicast between them,
+                                              5 = CTA pairs on 256 x 512 tiles (N a multiple of 512, else as 2)    */
   int32_t split_terms;                     /* operand precision: 2 = fp16 MMA + two e5m2 correction MMAs at fp8 rate
                                               (sizes must be multiples of 64), 3 = three bf16 MMA terms (A0W0 + A1W0
                                               + A0W1), 0 = auto (2 when the sizes allow it, else 3), 1 = one bf16

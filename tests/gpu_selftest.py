@@ -1,7 +1,7 @@
 """GPU self-test driver (run in a child process so that a kernel fault cannot poison the caller's CUDA context).
 
-    python tests/gpu_selftest.py gemm    --impl {1,2,3,4}
-    python tests/gpu_selftest.py forward --impl {1,2,3,4} [--configs tiny,tiny_lang,...] [--terms {1,2,3}]
+    python tests/gpu_selftest.py gemm    --impl {1,2,3,4,5}
+    python tests/gpu_selftest.py forward --impl {1,2,3,4,5} [--configs tiny,tiny_lang,...] [--terms {1,2,3}]
 
 Prints one JSON object per line: GEMM cases are checked against a float64 torch matmul of the SAME fp32 inputs,
 forward cases against the numpy oracle (oracle/hypernet_oracle.py).  ``tests/test_gpu_*.py`` assert on the lines.
@@ -168,6 +168,10 @@ def run_sustained(mnk_list, seconds=1.5):
             ("f16+2xe5m2 main term only", 2, 2, 1, True, {}),
             ("f16+2xe5m2 fp8 terms only", 2, 2, 4, True, {}),
             ("f16+2xe5m2 pairs of pairs", 4, 2, 7, True, {}),
+            ("f16+2xe5m2 256x512 tiles", 5, 2, 7, True, {}),
+            ("f16+2xe5m2 256x512 tiles no store", 5, 2, 7, False, {}),
+            ("f16+2xe5m2 256x512 tiles main term only", 5, 2, 1, True, {}),
+            ("bf16x3 256x512 tiles", 5, 3, 7, True, {}),
             ("bf16 single pass", 2, 1, 7, True, {}),
             ("bf16 single pass no store", 2, 1, 7, False, {}),
         ]

@@ -27,9 +27,9 @@ def run_selftest(args, timeout=900):
     return r, lines
 
 
-@pytest.mark.parametrize("impl", [3, 1, 2, 4])
+@pytest.mark.parametrize("impl", [3, 1, 2, 4, 5])
 def test_gemm_engine(impl):
-    """tcgen05 1-CTA / CTA pairs / pairs of pairs with W multicast, and the SIMT checker against float64 matmul: 3-term split within 5e-5 of max |ref|."""
+    """tcgen05 1-CTA / CTA pairs / pairs of pairs with W multicast / pairs on 256 x 512 tiles, and the SIMT checker against float64 matmul: 3-term split within 5e-5 of max |ref|."""
     r, lines = run_selftest(["gemm", "--impl", str(impl)])
     assert lines, r.stdout + r.stderr
     for ln in lines:
@@ -38,7 +38,7 @@ def test_gemm_engine(impl):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("impl", [3, 1, 2, 4])
+@pytest.mark.parametrize("impl", [3, 1, 2, 4, 5])
 def test_forward_tiny_configs(impl):
     """All tiny configurations (separate / tied heads, lang-id slot, single head, no rescale / bias, one layer,
     multi-pass) against the oracle: Frobenius and worst-row relative error <= 1e-3."""

@@ -19,6 +19,10 @@
 //    25 % fewer bytes are what lets the formats with fewer MMAs per byte reach the tensor pipe.  A smem stage of a CTA is
 //    then written by two CTAs, so every empty barrier counts one tcgen05.commit from EACH pair leader (multicast to all
 //    four CTAs); the full barriers stay per pair.
+//  * n_halves == 2 (gemm_impl 5) widens the tile of a CTA pair to 256 x 512: both accumulators of TMEM hold the two N halves
+//    of ONE tile, every k-block of A is fetched once for 512 columns (25 % fewer operand bytes per FLOP, the largest item of
+//    the kernel's energy budget after the MMAs), at the price of two 96 KB smem stages instead of
+//    three 64 KB ones and an epilogue that no longer overlaps the next tile's main loop.
 //  * M may live in device memory (packed-position counts are data dependent); tiles beyond it are skipped.
 #pragma once
 #include <cuda.h>
@@ -38,7 +42,8 @@ struct GemmShape {
   int m_host;          // rows of A / out when m_dev == nullptr
   const int* m_dev;    // optional device-resident row count
   int n, k;
-  int block_n;         // 32, 64, 128 or 256
+  int block_n;         // UMMA N: 32, 64, 128 or 256
+  int n_halves;        // 1: tile N = block_n, accumulators double-buffered; 2: tile N = 2 * block_n (block_n == 256 only)
   int group_m;         // rasterisation: m-tiles per group
   int chunk_n;         // rasterisation: n-tiles per L2-resident W chunk
   int block_k;         // K elements per pipeline stage: 64 (128-byte rows of 16-bit operands) or 32
@@ -105,12 +110,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int M = s.m_dev ? *s.m_dev : s.m_host;
   const int tile_m = kBlockM * CG * CP;                // rows of one cluster tile
   const int m_tiles = (M + tile_m - 1) / tile_m;
-  const int n_tiles = (s.n + s.block_n - 1) / s.block_n;
+  const int tile_n = s.block_n * s.n_halves;
+  const int n_tiles = (s.n + tile_n - 1) / tile_n;
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = (s.k + s.block_k - 1) / s.block_k;
   const int first_tile = blockIdx.x / (CG * CP);
   const int tile_step = gridDim.x / (CG * CP);
-  const int load_n = s.block_n / CG;  // rows of the W tile this CTA's smem holds
+  const int load_n = s.block_n / CG;  // rows of the W tile this CTA's smem holds, per N half
   const int cta_row0 = static_cast<int>(pair) * kBlockM * CG + static_cast<int>(cta_rank) * kBlockM;  // inside the cluster tile
 
   if (warp == 0 && lane == 0) {
@@ -145,7 +151,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
         const int row_a = tc.m_blk * tile_m + cta_row0;
-        const int row_b = tc.n_blk * s.block_n + static_cast<int>(cta_rank) * load_n;
+        const int row_b = tc.n_blk * tile_n + static_cast<int>(cta_rank) * load_n * s.n_halves;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
           const uint32_t a_dst = smem_base + stage * s.stage_bytes;
@@ -197,38 +203,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int iter = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1u;
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u, 2);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * s.block_n);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase, 3);
           tc_fence_after();
           const uint32_t a0 = smem_base + stage * s.stage_bytes;
           const uint32_t b0 = a0 + s.n_planes * s.a_plane_bytes;
           const uint32_t row16 = static_cast<uint32_t>(s.block_k) * 2u;  // bytes per row of a 16-bit plane
-          const uint64_t da0 = umma_desc_kmajor(a0, row16), db0 = umma_desc_kmajor(b0, row16);
-          const uint64_t da1 = umma_desc_kmajor(a0 + s.a_plane_bytes, row16), db1 = umma_desc_kmajor(b0 + s.b_plane_bytes, row16);
+          const uint64_t da0 = umma_desc_kmajor(a0, row16), da1 = umma_desc_kmajor(a0 + s.a_plane_bytes, row16);
+          const uint32_t a8 = b0 + s.n_planes * s.b_plane_bytes;
+          const uint64_t dqa = umma_desc_kmajor(a8, 128u);
           const int ksteps = s.block_k / kUmmaK;
-#pragma unroll 4
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
-            if (s.mma_mask & 1) umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
-            if (s.n_terms == 3 && !s.f8 && (s.mma_mask & 2)) {
-              umma_f16<CG>(tmem_d, da1 + koff, db0 + koff, s.idesc, 1u);
-              umma_f16<CG>(tmem_d, da0 + koff, db1 + koff, s.idesc, 1u);
+          for (int hf = 0; hf < s.n_halves; ++hf) {
+            // accumulator: the N half of the tile (n_halves == 2) or the buffer this tile alternates to (n_halves == 1)
+            const int acc = s.n_halves == 2 ? hf : (iter & 1);
+            if (kb == 0) {
+              const uint32_t acc_phase = s.n_halves == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
+              mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u, 2);
+              tc_fence_after();
             }
-          }
-          if (s.f8 && (s.mma_mask & 4)) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
-            const uint32_t a8 = b0 + s.n_planes * s.b_plane_bytes;
-            const uint64_t dqa = umma_desc_kmajor(a8, 128u), dqb = umma_desc_kmajor(a8 + s.a8_bytes, 128u);
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * s.block_n);
+            const uint32_t bh = b0 + static_cast<uint32_t>(hf * load_n) * row16;  // this half's rows of the W planes
+            const uint64_t db0 = umma_desc_kmajor(bh, row16), db1 = umma_desc_kmajor(bh + s.b_plane_bytes, row16);
+#pragma unroll 4
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
+              if (s.mma_mask & 1) umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
+              if (s.n_terms == 3 && !s.f8 && (s.mma_mask & 2)) {
+                umma_f16<CG>(tmem_d, da1 + koff, db0 + koff, s.idesc, 1u);
+                umma_f16<CG>(tmem_d, da0 + koff, db1 + koff, s.idesc, 1u);
+              }
+            }
+            if (s.f8 && (s.mma_mask & 4)) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
+              const uint64_t dqb = umma_desc_kmajor(a8 + s.a8_bytes + static_cast<uint32_t>(hf * load_n) * 128u, 128u);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)  // bytes [0, 64) of a row are q0 of the k-block, [64, 128) are q1
-              umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, (s.mma_mask & 1) | kb | kk);
+              for (int kk = 0; kk < 4; ++kk)  // bytes [0, 64) of a row are q0 of the k-block, [64, 128) are q1
+                umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, (s.mma_mask & 1) | kb | kk);
+            }
+            if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc), kPairMask);  // accumulator complete (this pair)
           }
-          umma_commit<CG>(empty_bar(stage), kAllMask);                      // frees the stage in every CTA of the cluster
-          if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc), kPairMask);  // accumulator complete (this pair)
+          umma_commit<CG>(empty_bar(stage), kAllMask);                            // frees the stage in every CTA of the cluster
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -239,30 +252,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1u;
-      mbar_wait(tmem_full_bar(acc), acc_phase, 4);
-      tc_fence_after();
       const int row = tc.m_blk * tile_m + cta_row0 + quarter * 32 + lane;
-      const int col_tile = tc.n_blk * s.block_n;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
-      // two register chunks: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed
-      float va[32], vb[32];
       const bool row_ok = row < M;
-      tmem_ld_32x32(taddr, va);
-      for (int c = 0; c < s.block_n; c += 64) {
-        tmem_ld_wait();
-        if (c + 32 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), vb);
-        if (row_ok && col_tile + c < s.n) epilogue_store32(ep, row, col_tile + c, min(32, s.n - col_tile - c), va);
-        if (c + 32 < s.block_n) {
+      for (int hf = 0; hf < s.n_halves; ++hf) {
+        const int acc = s.n_halves == 2 ? hf : (iter & 1);
+        const uint32_t acc_phase = s.n_halves == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
+        mbar_wait(tmem_full_bar(acc), acc_phase, 4);
+        tc_fence_after();
+        // accumulator column c holds W row (c < load_n ? CTA 0's : CTA 1's) share of this half:
+        //   output column = tile origin + (c / load_n) * load_n * n_halves + hf * load_n + c % load_n   (= origin + c when n_halves == 1)
+        const int col_tile = tc.n_blk * tile_n + hf * load_n;
+        auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (s.n_halves - 1)); };
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
+        // two register chunks: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed
+        float va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+        for (int c = 0; c < s.block_n; c += 64) {
           tmem_ld_wait();
-          if (c + 64 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 64), va);
-          if (row_ok && col_tile + c + 32 < s.n) epilogue_store32(ep, row, col_tile + c + 32, min(32, s.n - col_tile - c - 32), vb);
+          if (c + 32 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), vb);
+          if (row_ok && gcol(c) < s.n) epilogue_store32(ep, row, gcol(c), min(32, s.n - gcol(c)), va);
+          if (c + 32 < s.block_n) {
+            tmem_ld_wait();
+            if (c + 64 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 64), va);
+            if (row_ok && gcol(c + 32) < s.n) epilogue_store32(ep, row, gcol(c + 32), min(32, s.n - gcol(c + 32)), vb);
+          }
         }
+        tc_fence_before();
+        if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
+        else mbar_arrive_cluster(tmem_empty_bar(acc), pair * CG);
       }
-      tc_fence_before();
-      if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
-      else mbar_arrive_cluster(tmem_empty_bar(acc), pair * CG);
     }
   }
 

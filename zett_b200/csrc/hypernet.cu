@@ -176,7 +176,8 @@ struct GemmArgs {
 
 struct GemmEngine {
   DeviceInfo dev;
-  int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 CTA pairs, 3: SIMT, 4: CTA pairs, two per cluster, W multicast
+  int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 CTA pairs, 3: SIMT, 4: CTA pairs, two per cluster, W multicast,
+                       // 5: CTA pairs on 256 x 512 tiles (both TMEM accumulators hold one tile)
   int max_clusters4 = -1;  // co-resident clusters of four CTAs (queried once; GPC sizes decide it)
   int n_terms = 3;     // 3: 16-bit three-term split, 1: single 16-bit pass, 2: fp16 + two e5m2 correction passes
   int split_fmt = kFmtBf16;
@@ -293,14 +294,15 @@ struct GemmEngine {
     GemmShape s{};
     s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
     s.block_n = pick_block_n(g.n);
+    s.n_halves = (impl == 5 && s.block_n == 256 && g.n % 512 == 0) ? 2 : 1;
     s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0; s.mma_mask = mma_mask;
     s.hint_a = hint_a; s.hint_b = hint_b;
     const int load_n = s.block_n / cg;
     s.block_k = block_k;
     s.a_plane_bytes = kBlockM * block_k * 2;
-    s.b_plane_bytes = static_cast<uint32_t>(load_n) * block_k * 2;
+    s.b_plane_bytes = static_cast<uint32_t>(load_n) * s.n_halves * block_k * 2;
     s.a8_bytes = f8 ? kBlockM * 128 : 0;
-    s.b8_bytes = f8 ? static_cast<uint32_t>(load_n) * 128 : 0;
+    s.b8_bytes = f8 ? static_cast<uint32_t>(load_n) * s.n_halves * 128 : 0;
     s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes) + s.a8_bytes + s.b8_bytes;
     s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack) / static_cast<int>(s.stage_bytes));
     if (s.num_stages < 2) return fail(ZETT_ERR_INVALID, "GEMM tile does not fit two pipeline stages");
@@ -312,17 +314,17 @@ struct GemmEngine {
     const CUtensorMap *ta, *tb, *ta8, *tb8;
     // with two pairs per cluster a CTA fetches half of its W share, one plane per copy (gemm_tcgen05.cuh)
     ZETT_TRY(tmap(g.a, g.a_rows, g.k, g.a_plane_stride, kBlockM, n_planes, n_planes, &ta));
-    ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n / cp, n_planes, cp == 2 ? 1 : n_planes, &tb));
+    ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n * s.n_halves / cp, n_planes, cp == 2 ? 1 : n_planes, &tb));
     ta8 = ta; tb8 = tb;
     if (f8) {
       ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, kBlockM, &ta8));
-      ZETT_TRY(tmap8(g.w_q, g.n, g.k, load_n / cp, &tb8));
+      ZETT_TRY(tmap8(g.w_q, g.n, g.k, load_n * s.n_halves / cp, &tb8));
     }
     const int tile_m = kBlockM * cg * cp;
     const long long m_tiles = (g.m_host + tile_m - 1) / tile_m;
-    const long long n_tiles = (g.n + s.block_n - 1) / s.block_n;
+    const long long n_tiles = (g.n + s.block_n * s.n_halves - 1) / (s.block_n * s.n_halves);
     // W chunk of <= ~48 MB (4 bytes per element in every multi-plane format) stays in the 126 MB L2 next to the A group
-    const long long w_tile_bytes = static_cast<long long>(s.block_n) * g.k * (n_terms == 1 ? 2 : 4);
+    const long long w_tile_bytes = static_cast<long long>(s.block_n) * s.n_halves * g.k * (n_terms == 1 ? 2 : 4);
     s.chunk_n = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, raster_chunk_bytes / std::max<long long>(w_tile_bytes, 1))));
     s.group_m = std::max(1, raster_group_m / cp);
     const long long tiles = m_tiles * n_tiles;
@@ -990,7 +992,7 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   int impl = cfg->gemm_impl;
   if (const char* e = getenv("ZETT_GEMM_IMPL")) impl = atoi(e);
   h->gemm.impl = impl == 0 ? 2 : impl;
-  if (h->gemm.impl < 1 || h->gemm.impl > 4) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..4"); }
+  if (h->gemm.impl < 1 || h->gemm.impl > 5) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..5"); }
   int terms = cfg->split_terms;
   if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
   // auto: fp16 + two e5m2 correction planes (fewest tensor-pipe cycles inside the 1e-3 budget) when every GEMM K is a
