@@ -71,7 +71,7 @@ typedef struct zett_hn_config {
   float encoder_layer_norm_eps;            /* 1e-5 (roberta-base)                                                  */
   /* execution knobs, not model semantics */
   int32_t max_rows_per_pass;               /* rows handled by one pass of the kernels (0 -> 16384, transfer.py:44) */
-  int32_t gemm_impl;                       /* 0 = auto, 1 = tcgen05 1-CTA, 2 = tcgen05 CTA pairs (cta_group::2),
+  int32_t gemm_impl;                       /* 0 = auto (5), 1 = tcgen05 1-CTA, 2 = tcgen05 CTA pairs (cta_group::2),
                                               3 = SIMT fp32 debug kernel (checker, never the default),
                                               4 = CTA pairs, two per cluster, W tile TMA-multicast between them,
                                               5 = CTA pairs on 256 x 512 tiles (N a multiple of 512, else as 2)    */

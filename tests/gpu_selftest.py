@@ -312,13 +312,13 @@ def main():
     args = ap.parse_args()
     if args.what == "one":
         m, n, k = [int(x) for x in args.mnk.split(",")]
-        ok = run_one(m, n, k, args.impl or 2, args.terms or 3)
+        ok = run_one(m, n, k, args.impl or 5, args.terms or 2)
     elif args.what == "sweep":
         ok = run_sweep()
     elif args.what == "sustained":
         ok = run_sustained([tuple(int(x) for x in t.split(",")) for t in args.mnk.split(";")])
     elif args.what == "gemm":
-        ok = run_gemm(args.impl or 2)
+        ok = run_gemm(args.impl or 5)
     else:
         ok = True
         for c in args.configs.split(","):

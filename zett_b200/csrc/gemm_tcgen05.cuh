@@ -12,6 +12,9 @@
 //    tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
 //  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the B tile; the
 //    leader alone arrives on the full barrier (expecting both CTAs' bytes), issues the MMAs and multicasts the commits.
+//  * eight epilogue warps, two per TMEM lane quarter: the two groups of four take alternate 32-column chunks of one
+//    accumulator, or one N half each when n_halves == 2 (the epilogue is instruction-issue bound -- GELU, format
+//    conversion, 16-byte stores -- and with K = 768 it is as long as the main loop of a tile).
 //  * CP == 2 puts two such pairs in one cluster of four CTAs working on vertically adjacent 256-row tiles of the same
 //    N tile: every CTA fetches only HALF of its pair's share of the W tile and TMA-multicasts it to the CTA holding the
 //    same share in the other pair (.multicast::cluster), so a cluster moves 4 A blocks + 2 W blocks through L2 -> SM
@@ -35,7 +38,8 @@ constexpr int kBlockM = 128;
 constexpr int kMaxBlockK = 64;      // 64 x 2 B = one 128-byte swizzle row; block_k = 32 halves the rows (more, finer stages)
 constexpr int kUmmaK = 16;
 constexpr int kMaxStages = 8;
-constexpr int kGemmThreads = 192;   // 6 warps
+constexpr int kEpilogueWarps = 8;    // two per TMEM lane quarter
+constexpr int kGemmThreads = 64 + 32 * kEpilogueWarps;   // TMA producer warp, MMA warp, epilogue warps
 constexpr uint32_t kTmemCols = 512;
 
 struct GemmShape {
@@ -132,7 +136,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar(i), 1);
-      mbar_init(tmem_empty_bar(i), 128 * CG);  // every epilogue thread of every CTA in the group
+      // every epilogue thread that reads this accumulator, in every CTA of the pair: both warp groups (n_halves == 1)
+      // or the one group that owns this N half (n_halves == 2)
+      mbar_init(tmem_empty_bar(i), (s.n_halves == 2 ? 128 : 256) * CG);
     }
     fence_barrier_init();
   }
@@ -248,39 +254,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ===================================== epilogue warps ========================================
-    const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32) are the ones this warp may read
+    const int quarter = warp & 3;        // TMEM lanes [32 * quarter, 32 * quarter + 32) are the ones this warp may read
+    const int group = (warp - 2) >> 2;   // 0 or 1
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
       const int row = tc.m_blk * tile_m + cta_row0 + quarter * 32 + lane;
       const bool row_ok = row < M;
-      for (int hf = 0; hf < s.n_halves; ++hf) {
-        const int acc = s.n_halves == 2 ? hf : (iter & 1);
-        const uint32_t acc_phase = s.n_halves == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
-        mbar_wait(tmem_full_bar(acc), acc_phase, 4);
-        tc_fence_after();
-        // accumulator column c holds W row (c < load_n ? CTA 0's : CTA 1's) share of this half:
-        //   output column = tile origin + (c / load_n) * load_n * n_halves + hf * load_n + c % load_n   (= origin + c when n_halves == 1)
-        const int col_tile = tc.n_blk * tile_n + hf * load_n;
-        auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (s.n_halves - 1)); };
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
-        // two register chunks: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed
-        float va[32], vb[32];
-        tmem_ld_32x32(taddr, va);
-        for (int c = 0; c < s.block_n; c += 64) {
+      // n_halves == 2: group g drains N half g.  n_halves == 1: both groups drain the tile's accumulator, group g taking
+      // the 32-column chunks g, g + 2, ...
+      const int hf = s.n_halves == 2 ? group : 0;
+      const int acc = s.n_halves == 2 ? hf : (iter & 1);
+      const uint32_t acc_phase = s.n_halves == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
+      const int c_first = s.n_halves == 2 ? 0 : 32 * group;
+      const int c_step = s.n_halves == 2 ? 32 : 64;
+      mbar_wait(tmem_full_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      // accumulator column c holds W row (c < load_n ? CTA 0's : CTA 1's) share of this half:
+      //   output column = tile origin + (c / load_n) * load_n * n_halves + hf * load_n + c % load_n   (= origin + c when n_halves == 1)
+      const int col_tile = tc.n_blk * tile_n + hf * load_n;
+      auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (s.n_halves - 1)); };
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
+      // two register chunks: the tcgen05.ld of the next chunk is in flight while the current one is processed
+      float va[32], vb[32];
+      if (c_first < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c_first), va);
+      for (int c = c_first; c < s.block_n; c += 2 * c_step) {
+        const int c2 = c + c_step, c3 = c2 + c_step;
+        tmem_ld_wait();
+        if (c2 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c2), vb);
+        if (row_ok && gcol(c) < s.n) epilogue_store32(ep, row, gcol(c), min(32, s.n - gcol(c)), va);
+        if (c2 < s.block_n) {
           tmem_ld_wait();
-          if (c + 32 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 32), vb);
-          if (row_ok && gcol(c) < s.n) epilogue_store32(ep, row, gcol(c), min(32, s.n - gcol(c)), va);
-          if (c + 32 < s.block_n) {
-            tmem_ld_wait();
-            if (c + 64 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + 64), va);
-            if (row_ok && gcol(c + 32) < s.n) epilogue_store32(ep, row, gcol(c + 32), min(32, s.n - gcol(c + 32)), vb);
-          }
+          if (c3 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c3), va);
+          if (row_ok && gcol(c2) < s.n) epilogue_store32(ep, row, gcol(c2), min(32, s.n - gcol(c2)), vb);
         }
-        tc_fence_before();
-        if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
-        else mbar_arrive_cluster(tmem_empty_bar(acc), pair * CG);
       }
+      tc_fence_before();
+      if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
+      else mbar_arrive_cluster(tmem_empty_bar(acc), pair * CG);
     }
   }
 

@@ -176,7 +176,7 @@ struct GemmArgs {
 
 struct GemmEngine {
   DeviceInfo dev;
-  int impl = 2;        // 1: tcgen05 1-CTA, 2: tcgen05 CTA pairs, 3: SIMT, 4: CTA pairs, two per cluster, W multicast,
+  int impl = 5;        // 1: tcgen05 1-CTA, 2: tcgen05 CTA pairs, 3: SIMT, 4: CTA pairs, two per cluster, W multicast,
                        // 5: CTA pairs on 256 x 512 tiles (both TMEM accumulators hold one tile)
   int max_clusters4 = -1;  // co-resident clusters of four CTAs (queried once; GPC sizes decide it)
   int n_terms = 3;     // 3: 16-bit three-term split, 1: single 16-bit pass, 2: fp16 + two e5m2 correction passes
@@ -461,7 +461,7 @@ struct Workspace {
   std::vector<void*> allocs;
   size_t bytes = 0;
   // pack metadata
-  int *counts_all = nullptr, *row_start1 = nullptr, *row_start2 = nullptr, *tok_src = nullptr, *tok_pos = nullptr,
+  int *counts_all = nullptr, *row_cnt = nullptr, *row_start1 = nullptr, *row_start2 = nullptr, *tok_id = nullptr, *tok_pos = nullptr,
       *tok_enc = nullptr, *tok1_row = nullptr, *lang_enc = nullptr, *tok2_row = nullptr, *id_claim = nullptr,
       *id_slot = nullptr, *uniq_src = nullptr, *tok_u = nullptr, *pair_claim = nullptr, *pair_slot = nullptr,
       *pair_u = nullptr, *pair_pos = nullptr, *enc_pair = nullptr;
@@ -529,7 +529,7 @@ size_t workspace_bytes_for(const zett_hn* h, long long rows) {
   size_t b = 0;
   const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
   b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 6 * t1 + rows + t2 + 2 * n_ids) + t2;
-  b += sizeof(int) * (2 * std::min<long long>(t1, n_ids) * h->L + 2 * (t1 + 1) + t2);  // distinct (id, position) pairs
+  b += sizeof(int) * (2 * n_ids * h->L + 2 * (t1 + 1) + t2 + rows);  // distinct (id, position) pairs, per-row counts
   b += 2ull * 2 * std::min<long long>(t1, n_ids) * E;  // P_E
   b += 2ull * 2 * t2 * H * 2;             // PH_a, PH_b
   b += 2ull * 2 * t2 * I;                 // PI
@@ -548,7 +548,8 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.counts_all, kMaxPassSlots * kCntSlots);
   WS_ALLOC(w.row_start1, rows + 1);
   WS_ALLOC(w.row_start2, rows + 1);
-  WS_ALLOC(w.tok_src, t1);
+  WS_ALLOC(w.row_cnt, rows);
+  WS_ALLOC(w.tok_id, t1);
   WS_ALLOC(w.tok_pos, t1);
   WS_ALLOC(w.tok_enc, t1);
   WS_ALLOC(w.tok1_row, t1);
@@ -561,8 +562,8 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.id_slot, n_ids);
   WS_ALLOC(w.uniq_src, w.uniq_cap);
   WS_ALLOC(w.tok_u, t1);
-  WS_ALLOC(w.pair_claim, w.uniq_cap * h->L);
-  WS_ALLOC(w.pair_slot, w.uniq_cap * h->L);
+  WS_ALLOC(w.pair_claim, n_ids * h->L);
+  WS_ALLOC(w.pair_slot, n_ids * h->L);
   WS_ALLOC(w.pair_u, t1 + 1);
   WS_ALLOC(w.pair_pos, t1 + 1);
   WS_ALLOC(w.enc_pair, t2);
@@ -762,18 +763,26 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
   PackParams pp{};
   pp.ids = ids; pp.n_rows = rows; pp.L = L; pp.pad_id = h->cfg.pad_token_id; pp.v0 = h->cfg.original_vocab_size;
   pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.counts = counts;
-  pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_src = w.tok_src; pp.tok_pos = w.tok_pos;
+  pp.row_cnt = w.row_cnt; pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_id = w.tok_id; pp.tok_pos = w.tok_pos;
   pp.tok_enc = w.tok_enc; pp.tok1_row = w.tok1_row; pp.lang_enc = w.lang_enc; pp.tok2_row = w.tok2_row; pp.tok2_valid = w.tok2_valid;
   pp.id_claim = w.id_claim; pp.id_slot = w.id_slot; pp.uniq_src = w.uniq_src; pp.tok_u = w.tok_u;
   // the first encoder layer runs on distinct (id, position) pairs unless it is also the (pruned) last one
   const bool pairs = h->dedup_pairs && n_layers > 1;
   if (pairs) {
-    ZETT_CUDA(cudaMemsetAsync(w.pair_claim, 0x7F, sizeof(int) * static_cast<size_t>(capu) * L, stream));
+    ZETT_CUDA(cudaMemsetAsync(w.pair_claim, 0x7F, sizeof(int) * (static_cast<size_t>(h->cfg.original_vocab_size) + h->n_fallback) * L, stream));
     pp.pair_claim = w.pair_claim; pp.pair_slot = w.pair_slot; pp.pair_u = w.pair_u; pp.pair_pos = w.pair_pos; pp.enc_pair = w.enc_pair;
   }
-  pack_rows_kernel<<<1, kPackThreads, 0, stream>>>(pp);
-  ZETT_CUDA(cudaGetLastError());
-  ++h->gemm.launches;
+  {
+    const int row_blocks = (rows + kPackBlock - 1) / kPackBlock;
+    const int pos_blocks = static_cast<int>((static_cast<long long>(rows) * L + 1 + kPackBlock - 1) / kPackBlock);
+    pack_count_kernel<<<row_blocks, kPackBlock, 0, stream>>>(pp);
+    pack_scan_kernel<<<1, kPackThreads, 0, stream>>>(pp);
+    pack_emit_kernel<<<row_blocks, kPackBlock, 0, stream>>>(pp);
+    pack_owner_kernel<<<pos_blocks, kPackBlock, 0, stream>>>(pp);
+    pack_index_kernel<<<pos_blocks, kPackBlock, 0, stream>>>(pp);
+    ZETT_CUDA(cudaGetLastError());
+    h->gemm.launches += 5;
+  }
 
   // ---- gather + in_scaler + split  (modeling_hypernet.py:170-188) ------------------------------------------------
   {
@@ -991,7 +1000,7 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   if (rc != ZETT_OK) { delete h; return rc; }
   int impl = cfg->gemm_impl;
   if (const char* e = getenv("ZETT_GEMM_IMPL")) impl = atoi(e);
-  h->gemm.impl = impl == 0 ? 2 : impl;
+  h->gemm.impl = impl == 0 ? 5 : impl;
   if (h->gemm.impl < 1 || h->gemm.impl > 5) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..5"); }
   int terms = cfg->split_terms;
   if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
@@ -1220,7 +1229,7 @@ int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev,
   GemmEngine eng;
   ZETT_TRY(query_device(&eng.dev));
   ZETT_TRY(set_kernel_attrs(&eng.dev));
-  eng.impl = impl == 0 ? 2 : impl;
+  eng.impl = impl == 0 ? 5 : impl;
   eng.set_precision(split_terms);
   eng.read_env();
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);

@@ -21,7 +21,8 @@
 
 namespace zett {
 
-constexpr int kPackThreads = 1024;
+constexpr int kPackThreads = 1024;   // the single-block scan
+constexpr int kPackBlock = 256;      // the per-row / per-position kernels
 constexpr int kMaxSurfaceLen = 32;
 
 // counts[] slots
@@ -32,10 +33,11 @@ struct PackParams {
   int n_rows, L;
   int pad_id, v0, n_fallback;  // n_fallback = max(hn_n_extra_tokens, 1)
   int lang_slot;               // 1 when a lang-id position is appended to every row
-  int* counts;                 // [kCntSlots]
+  int* counts;                 // [kCntSlots], zeroed before the pass
+  int* row_cnt;                // [n_rows]      kept positions of each row
   int* row_start1;             // [n_rows + 1]  surface packing (input projection)
   int* row_start2;             // [n_rows + 1]  encoder packing (surface positions + lang slot)
-  int* tok_src;                // [T1]  >= 0: source row, < 0: -1 - fallback row
+  int* tok_id;                 // [T1]  clamped id of each kept position
   int* tok_pos;                // [T1]  position id
   int* tok_enc;                // [T1]  index of this position in the encoder packing
   int* tok1_row;               // [T1]  row of this position
@@ -46,13 +48,13 @@ struct PackParams {
   // evaluated once per DISTINCT id of the pass
   int* id_claim;               // [v0 + n_fallback] scratch, preset to INT_MAX-like: lowest position holding the id
   int* id_slot;                // [v0 + n_fallback] scratch: index of the id among the distinct ids
-  int* uniq_src;               // [U]   tok_src code of each distinct id, in order of first occurrence
+  int* uniq_src;               // [U]   source row (>= 0) or -1 - fallback row (< 0) of each distinct id
   int* tok_u;                  // [T1]  index into the distinct ids
   // de-duplication of the first encoder layer's input: LayerNorm(projection[id] + type + position[pos]) and the
   // query/key/value rows computed from it depend on the (id, position) pair only, so they are evaluated once per
-  // DISTINCT pair of the pass (nullable: pair_claim == nullptr switches this off)
-  int* pair_claim;             // [U_cap * L] scratch, preset to INT_MAX-like: lowest position holding the pair
-  int* pair_slot;              // [U_cap * L] scratch: index of the pair among the distinct pairs
+  // DISTINCT pair of the pass (pair_claim == nullptr switches this off)
+  int* pair_claim;             // [(v0 + n_fallback) * L] scratch, preset to INT_MAX-like: lowest position holding the pair
+  int* pair_slot;              // [(v0 + n_fallback) * L] scratch: index of the pair among the distinct pairs
   int* pair_u;                 // [P]   distinct-id index of each distinct pair   (slot 0 = the lang-id position when lang_slot)
   int* pair_pos;               // [P]   position id of each distinct pair
   int* enc_pair;               // [T2]  distinct-pair index of every encoder position
@@ -66,26 +68,32 @@ __device__ __forceinline__ uint32_t kept_mask(const int32_t* row, int L, int pad
   return kept;
 }
 
-// One block; thread i owns a contiguous slice of rows.  Two walks over the slice: count, block scan, emit.
-__global__ void __launch_bounds__(kPackThreads, 1) pack_rows_kernel(const PackParams p) {
-  __shared__ int warp_sums[32];
-  __shared__ int warp_sums2[32];
-  const int tid = threadIdx.x;
-  const int rows_per_thread = (p.n_rows + kPackThreads - 1) / kPackThreads;
-  const int r0 = min(p.n_rows, tid * rows_per_thread);
-  const int r1 = min(p.n_rows, r0 + rows_per_thread);
-  const int id_limit = p.v0 + p.n_fallback;
+// The packing runs as five small grid-wide kernels on the caller's stream (a single block took 0.7 ms per 16 384 rows,
+// 11 % of a whole XLM-R-shape step).  Slots of distinct ids / pairs are handed out by atomic counters, so their ORDER
+// varies from run to run; the outputs do not (every GEMM / LayerNorm row is computed independently of its index).
 
-  int local = 0;
+// (1) one thread per row: kept positions, id range check
+__global__ void __launch_bounds__(kPackBlock) pack_count_kernel(const PackParams p) {
+  const int r = blockIdx.x * kPackBlock + threadIdx.x;
+  if (r >= p.n_rows) return;
+  const int32_t* row = p.ids + static_cast<long long>(r) * p.L;
+  const int id_limit = p.v0 + p.n_fallback;
+  uint32_t nonpad;
+  p.row_cnt[r] = __popc(kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad));
   int bad = 0;
-  for (int r = r0; r < r1; ++r) {
-    const int32_t* row = p.ids + static_cast<long long>(r) * p.L;
-    uint32_t nonpad;
-    local += __popc(kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad));
-    for (int q = 0; q < p.L; ++q) bad |= (row[q] < 0 || row[q] >= id_limit) ? 1 : 0;
-  }
-  // block-wide exclusive scan of `local`
-  const int lane = tid & 31, warp = tid >> 5;
+  for (int q = 0; q < p.L; ++q) bad |= (row[q] < 0 || row[q] >= id_limit) ? 1 : 0;
+  if (bad) atomicOr(&p.counts[kCntBadId], 1);
+}
+
+// (2) one block: exclusive scan of the per-row counts -> row starts of both packings, totals
+__global__ void __launch_bounds__(kPackThreads, 1) pack_scan_kernel(const PackParams p) {
+  __shared__ int warp_sums[32];
+  __shared__ int warp_excl[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (p.n_rows + kPackThreads - 1) / kPackThreads;
+  const int r0 = min(p.n_rows, tid * per), r1 = min(p.n_rows, r0 + per);
+  int local = 0;
+  for (int r = r0; r < r1; ++r) local += p.row_cnt[r];
   int incl = local;
   for (int o = 1; o < 32; o <<= 1) {
     const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -94,127 +102,92 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_rows_kernel(const PackPa
   if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    int w = warp_sums[lane];
+    const int w = warp_sums[lane];
     int wi = w;
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
       if (lane >= o) wi += t;
     }
-    warp_sums2[lane] = wi - w;  // exclusive prefix of the warp totals
+    warp_excl[lane] = wi - w;
     if (lane == 31) {
       p.counts[kCntSurface] = wi;
       p.counts[kCntEncoder] = wi + (p.lang_slot ? p.n_rows : 0);
       p.counts[kCntRows] = p.n_rows;
+      p.counts[kCntPairs] = (p.pair_claim && p.lang_slot) ? 1 : 0;  // pair 0 = the lang-id position
       p.row_start1[p.n_rows] = wi;
       p.row_start2[p.n_rows] = wi + (p.lang_slot ? p.n_rows : 0);
     }
   }
   __syncthreads();
-  if (bad) atomicOr(&p.counts[kCntBadId], 1);
-  int t1 = warp_sums2[warp] + incl - local;  // first surface position of row r0
-
+  int t1 = warp_excl[warp] + incl - local;
   for (int r = r0; r < r1; ++r) {
-    const int32_t* row = p.ids + static_cast<long long>(r) * p.L;
-    uint32_t nonpad;
-    const uint32_t kept = kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad);
-    const int t2_base = t1 + (p.lang_slot ? r : 0);
     p.row_start1[r] = t1;
-    p.row_start2[r] = t2_base;
-    int j = 0;
-    for (int q = 0; q < p.L; ++q) {
-      if (!((kept >> q) & 1u)) continue;
-      int id = row[q];
-      id = max(0, min(id, id_limit - 1));  // never read out of bounds; kCntBadId reports the violation
-      p.tok_src[t1 + j] = id;  // provisional: the id itself, recoded below
-      atomicMin(&p.id_claim[id], t1 + j);
-      p.tok_pos[t1 + j] = q;
-      p.tok_enc[t1 + j] = t2_base + j;
-      p.tok1_row[t1 + j] = r;
-      p.tok2_row[t2_base + j] = r;
-      p.tok2_valid[t2_base + j] = static_cast<unsigned char>((nonpad >> q) & 1u);
-      ++j;
-    }
-    if (p.lang_slot) {
-      p.lang_enc[r] = t2_base + j;
-      p.tok2_row[t2_base + j] = r;
-      p.tok2_valid[t2_base + j] = 1;
-    }
-    t1 += j;
+    p.row_start2[r] = t1 + (p.lang_slot ? r : 0);
+    t1 += p.row_cnt[r];
   }
-  // ---- distinct ids: owner = lowest position of each id; owners are numbered in position order -------------------
-  const int t_begin = warp_sums2[warp] + incl - local, t_end = t_begin + local;
-  __syncthreads();
-  int owners = 0;
-  for (int t = t_begin; t < t_end; ++t) owners += (__ldcg(&p.id_claim[p.tok_src[t]]) == t) ? 1 : 0;
-  int oincl = owners;
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xFFFFFFFFu, oincl, o);
-    if (lane >= o) oincl += v;
+}
+
+// (3) one thread per row: position lists of both packings; every position bids for its id and its (id, position) pair
+__global__ void __launch_bounds__(kPackBlock) pack_emit_kernel(const PackParams p) {
+  const int r = blockIdx.x * kPackBlock + threadIdx.x;
+  if (r >= p.n_rows) return;
+  const int32_t* row = p.ids + static_cast<long long>(r) * p.L;
+  const int id_limit = p.v0 + p.n_fallback;
+  uint32_t nonpad;
+  const uint32_t kept = kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad);
+  const int t1 = p.row_start1[r], t2 = p.row_start2[r];
+  int j = 0;
+  for (int q = 0; q < p.L; ++q) {
+    if (!((kept >> q) & 1u)) continue;
+    const int id = max(0, min(row[q], id_limit - 1));  // never read out of bounds; kCntBadId reports the violation
+    p.tok_id[t1 + j] = id;
+    p.tok_pos[t1 + j] = q;
+    p.tok_enc[t1 + j] = t2 + j;
+    p.tok1_row[t1 + j] = r;
+    p.tok2_row[t2 + j] = r;
+    p.tok2_valid[t2 + j] = static_cast<unsigned char>((nonpad >> q) & 1u);
+    atomicMin(&p.id_claim[id], t1 + j);
+    if (p.pair_claim) atomicMin(&p.pair_claim[id * p.L + q], t1 + j);
+    ++j;
   }
-  if (lane == 31) warp_sums[warp] = oincl;
-  __syncthreads();
-  if (warp == 0) {
-    const int w = warp_sums[lane];
-    int wi = w;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-      if (lane >= o) wi += v;
-    }
-    warp_sums2[lane] = wi - w;
-    if (lane == 31) p.counts[kCntUnique] = wi;
+  if (p.lang_slot) {
+    p.lang_enc[r] = t2 + j;
+    p.tok2_row[t2 + j] = r;
+    p.tok2_valid[t2 + j] = 1;
+    if (p.pair_claim) p.enc_pair[t2 + j] = 0;
   }
-  __syncthreads();
-  int u = warp_sums2[warp] + oincl - owners;
-  for (int t = t_begin; t < t_end; ++t) {
-    const int id = p.tok_src[t];
-    if (__ldcg(&p.id_claim[id]) == t) {
-      p.id_slot[id] = u;
-      p.uniq_src[u] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
-      ++u;
-    }
+}
+
+// (4) one thread per surface position: the lowest position holding an id / a pair owns it and takes the next free slot
+__global__ void __launch_bounds__(kPackBlock) pack_owner_kernel(const PackParams p) {
+  const int t = blockIdx.x * kPackBlock + threadIdx.x;
+  if (t == 0 && p.pair_claim && p.lang_slot) { p.pair_u[0] = 0; p.pair_pos[0] = 0; }  // placeholder, overwritten by the lang-id LayerNorm
+  if (t >= p.counts[kCntSurface]) return;
+  const int id = p.tok_id[t];
+  if (p.id_claim[id] == t) {
+    const int u = atomicAdd(&p.counts[kCntUnique], 1);
+    p.id_slot[id] = u;
+    p.uniq_src[u] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
   }
-  __syncthreads();
-  for (int t = t_begin; t < t_end; ++t) p.tok_u[t] = __ldcg(&p.id_slot[p.tok_src[t]]);
-  if (!p.pair_claim) return;
-  // ---- distinct (id, position) pairs: same owner scheme over the key  distinct-id index * L + position ----------
-  for (int t = t_begin; t < t_end; ++t) atomicMin(&p.pair_claim[p.tok_u[t] * p.L + p.tok_pos[t]], t);
-  __syncthreads();
-  int powners = 0;
-  for (int t = t_begin; t < t_end; ++t) powners += (__ldcg(&p.pair_claim[p.tok_u[t] * p.L + p.tok_pos[t]]) == t) ? 1 : 0;
-  int pincl = powners;
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xFFFFFFFFu, pincl, o);
-    if (lane >= o) pincl += v;
-  }
-  if (lane == 31) warp_sums[warp] = pincl;
-  __syncthreads();
-  const int pair_base = p.lang_slot ? 1 : 0;  // slot 0 is the lang-id position, identical for every row
-  if (warp == 0) {
-    const int w = warp_sums[lane];
-    int wi = w;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-      if (lane >= o) wi += v;
-    }
-    warp_sums2[lane] = wi - w;
-    if (lane == 31) p.counts[kCntPairs] = wi + pair_base;
-    if (lane == 0 && pair_base) { p.pair_u[0] = 0; p.pair_pos[0] = 0; }  // placeholder row, overwritten by the lang-id LayerNorm
-  }
-  __syncthreads();
-  int pu = pair_base + warp_sums2[warp] + pincl - powners;
-  for (int t = t_begin; t < t_end; ++t) {
-    const int key = p.tok_u[t] * p.L + p.tok_pos[t];
-    if (__ldcg(&p.pair_claim[key]) == t) {
-      p.pair_slot[key] = pu;
-      p.pair_u[pu] = p.tok_u[t];
-      p.pair_pos[pu] = p.tok_pos[t];
-      ++pu;
+  if (p.pair_claim) {
+    const int pos = p.tok_pos[t];
+    if (p.pair_claim[id * p.L + pos] == t) {
+      const int pu = atomicAdd(&p.counts[kCntPairs], 1);
+      p.pair_slot[id * p.L + pos] = pu;
+      p.pair_u[pu] = id;  // the id for now; pack_index_kernel turns it into the distinct-id index
+      p.pair_pos[pu] = pos;
     }
   }
-  __syncthreads();
-  for (int t = t_begin; t < t_end; ++t) p.enc_pair[p.tok_enc[t]] = __ldcg(&p.pair_slot[p.tok_u[t] * p.L + p.tok_pos[t]]);
-  if (p.lang_slot)
-    for (int r = r0; r < r1; ++r) p.enc_pair[p.lang_enc[r]] = 0;
+}
+
+// (5) one thread per surface position (and per distinct pair): indices into the distinct ids / pairs
+__global__ void __launch_bounds__(kPackBlock) pack_index_kernel(const PackParams p) {
+  const int t = blockIdx.x * kPackBlock + threadIdx.x;
+  if (p.pair_claim && t >= (p.lang_slot ? 1 : 0) && t < p.counts[kCntPairs]) p.pair_u[t] = p.id_slot[p.pair_u[t]];
+  if (t >= p.counts[kCntSurface]) return;
+  const int id = p.tok_id[t];
+  p.tok_u[t] = p.id_slot[id];
+  if (p.pair_claim) p.enc_pair[p.tok_enc[t]] = p.pair_slot[id * p.L + p.tok_pos[t]];
 }
 
 // -------------------------------------------------------------------------------------------------------------------
