@@ -229,69 +229,6 @@ __device__ __forceinline__ void epilogue_full32(const EpilogueParams& ep, int ro
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Warp-cooperative variant for the tensor-core kernel.  Lane l enters with accumulator row (row0 + l), columns
-// [col0, col0 + 32).  Stores straight from that layout are 32 separate 16-byte transactions per instruction (one per
-// row): measured at ~10 % of a GEMM's energy and fully exposed when the epilogue does not overlap the main loop.  So:
-// bias + activation in the accumulator layout (bias loads are warp-uniform), transpose the 32 x 32 block through 4 KB of
-// this warp's shared memory (float4 (r, c4) at r * 8 + (c4 ^ (r & 7)): conflict-free both ways), then every instruction
-// handles 4 rows x 128 contiguous bytes: residual reads, Rescaler affine and all stores are whole-line accesses.
-// ---------------------------------------------------------------------------------------------------------------
-template <int ACT>
-__device__ __forceinline__ void epilogue_warp32_impl(const EpilogueParams& ep, int row0, int m_rows, int col0, float (&v)[32],
-                                                     float4* s4, int lane) {
-  if (ep.bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b = __ldg(b4 + q);
-      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-    }
-  }
-  if (ACT == kActGeluTanh) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-  } else if (ACT == kActGeluErf) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
-  }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) s4[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  __syncwarp();
-  const int c4 = lane & 7, rsub = lane >> 3;
-  const int col = col0 + 4 * c4;
-  float4 sw = make_float4(1.f, 1.f, 1.f, 1.f), sb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.col_scale) {
-    sw = __ldg(reinterpret_cast<const float4*>(ep.col_scale + col));
-    sb = __ldg(reinterpret_cast<const float4*>(ep.col_shift + col));
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int r = 4 * j + rsub;
-    float4 y = s4[r * 8 + (c4 ^ (r & 7))];
-    const int row = row0 + r;
-    if (row < m_rows) {
-      if (ep.residual) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(ep.residual + static_cast<long long>(row) * ep.ld_res + col));
-        y.x += t.x; y.y += t.y; y.z += t.z; y.w += t.w;
-      }
-      if (ep.col_scale) {  // Rescaler: w * y + b with two roundings, as torch evaluates it (modeling_hypernet.py:18-19)
-        y.x = __fadd_rn(__fmul_rn(sw.x, y.x), sb.x); y.y = __fadd_rn(__fmul_rn(sw.y, y.y), sb.y);
-        y.z = __fadd_rn(__fmul_rn(sw.z, y.z), sb.z); y.w = __fadd_rn(__fmul_rn(sw.w, y.w), sb.w);
-      }
-      if (ep.out_f32) {
-        float4* o = reinterpret_cast<float4*>(ep.out_f32 + static_cast<long long>(row) * ep.ld_out + col);
-        if (ep.stream_f32) __stcs(o, y); else *o = y;
-      }
-      if (ep.out_p0) {
-        const float yy[4] = {y.x, y.y, y.z, y.w};
-        store_operand4(ep.out_p0, ep.out_p1, static_cast<long long>(row) * ep.ld_split + col, yy, ep.split_fmt, false);
-      }
-    }
-  }
-  __syncwarp();  // the block is consumed before the next chunk overwrites it
-}
-
 // ragged tail (N not a multiple of 32): element-wise, rarely taken
 __device__ __noinline__ void epilogue_ragged(const EpilogueParams& ep, int row, int col0, int ncols, const float* v) {
   for (int j = 0; j < ncols; ++j) {
@@ -316,21 +253,6 @@ __device__ __forceinline__ void epilogue_store32(const EpilogueParams& ep, int r
 #pragma unroll
     for (int j = 0; j < 32; ++j) t[j] = v[j];
     epilogue_ragged(ep, row, col0, ncols, t);
-  }
-}
-
-// all 32 lanes of the warp call this together; `scratch` = this warp's 4 KB of shared memory
-__device__ __forceinline__ void epilogue_warp_store32(const EpilogueParams& ep, int row0, int m_rows, int col0, int ncols,
-                                                      float (&v)[32], float4* scratch, int lane) {
-  if (ncols == 32) {
-    if (ep.act == kActGeluTanh) epilogue_warp32_impl<kActGeluTanh>(ep, row0, m_rows, col0, v, scratch, lane);
-    else if (ep.act == kActGeluErf) epilogue_warp32_impl<kActGeluErf>(ep, row0, m_rows, col0, v, scratch, lane);
-    else epilogue_warp32_impl<kActNone>(ep, row0, m_rows, col0, v, scratch, lane);
-  } else if (row0 + lane < m_rows) {
-    float t[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) t[j] = v[j];
-    epilogue_ragged(ep, row0 + lane, col0, ncols, t);
   }
 }
 

@@ -41,8 +41,6 @@ constexpr int kMaxStages = 8;
 constexpr int kEpilogueWarps = 8;    // two per TMEM lane quarter
 constexpr int kGemmThreads = 64 + 32 * kEpilogueWarps;   // TMA producer warp, MMA warp, epilogue warps
 constexpr uint32_t kTmemCols = 512;
-constexpr int kGemmBarrierBytes = 256;                       // mbarriers + the TMEM base slot
-constexpr int kGemmEpilogueBytes = kEpilogueWarps * 4096;   // one 32 x 32 fp32 transposition block per epilogue warp
 
 struct GemmShape {
   int m_host;          // rows of A / out when m_dev == nullptr
@@ -105,8 +103,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tmem_full_bar = [&](int i) { return bar_base + 8u * (2 * kMaxStages + i); };
   auto tmem_empty_bar = [&](int i) { return bar_base + 8u * (2 * kMaxStages + 2 + i); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
-  // per-warp 4 KB transposition blocks of the epilogue live behind the barriers
-  float4* const epi_scratch = reinterpret_cast<float4*>(smem_raw + (bar_base - smem_u32(smem_raw)) + kGemmBarrierBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -260,11 +256,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================================== epilogue warps ========================================
     const int quarter = warp & 3;        // TMEM lanes [32 * quarter, 32 * quarter + 32) are the ones this warp may read
     const int group = (warp - 2) >> 2;   // 0 or 1
-    float4* const scratch = epi_scratch + (warp - 2) * 256;
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
-      const int row0 = tc.m_blk * tile_m + cta_row0 + quarter * 32;  // lane l holds accumulator row row0 + l
+      const int row = tc.m_blk * tile_m + cta_row0 + quarter * 32 + lane;
+      const bool row_ok = row < M;
       // n_halves == 2: group g drains N half g.  n_halves == 1: both groups drain the tile's accumulator, group g taking
       // the 32-column chunks g, g + 2, ...
       const int hf = s.n_halves == 2 ? group : 0;
@@ -286,11 +282,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int c2 = c + c_step, c3 = c2 + c_step;
         tmem_ld_wait();
         if (c2 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c2), vb);
-        if (gcol(c) < s.n) epilogue_warp_store32(ep, row0, M, gcol(c), min(32, s.n - gcol(c)), va, scratch, lane);
+        if (row_ok && gcol(c) < s.n) epilogue_store32(ep, row, gcol(c), min(32, s.n - gcol(c)), va);
         if (c2 < s.block_n) {
           tmem_ld_wait();
           if (c3 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c3), va);
-          if (gcol(c2) < s.n) epilogue_warp_store32(ep, row0, M, gcol(c2), min(32, s.n - gcol(c2)), vb, scratch, lane);
+          if (row_ok && gcol(c2) < s.n) epilogue_store32(ep, row, gcol(c2), min(32, s.n - gcol(c2)), vb);
         }
       }
       tc_fence_before();

@@ -130,7 +130,7 @@ int query_device(DeviceInfo* d) {
 }
 
 constexpr int kMaxDynSmem = 232448;  // 227 KB
-constexpr int kGemmSmemSlack = 1024 /* alignment */ + kGemmBarrierBytes + kGemmEpilogueBytes;
+constexpr int kGemmSmemSlack = 1024 /* alignment */ + 256 /* barriers + tmem slot */;
 
 unsigned long long* g_watchdog_host = nullptr;  // pinned, device-mapped; survives a trapped context
 
