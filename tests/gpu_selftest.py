@@ -170,11 +170,15 @@ def run_sustained(mnk_list, seconds=1.5):
             ("f16+2xe5m2 pairs of pairs", 4, 2, 7, True, {}),
             ("f16+2xe5m2 256x512 tiles", 5, 2, 7, True, {}),
             ("f16+2xe5m2 256x512 tiles no store", 5, 2, 7, False, {}),
+            ("f16+2xe5m2 no store", 2, 2, 7, False, {}),
             ("f16+2xe5m2 256x512 tiles main term only", 5, 2, 1, True, {}),
             ("bf16x3 256x512 tiles", 5, 3, 7, True, {}),
             ("bf16 single pass", 2, 1, 7, True, {}),
             ("bf16 single pass no store", 2, 1, 7, False, {}),
         ]
+        only = os.environ.get("ZETT_SUSTAINED_ONLY")  # comma-separated substrings of the labels to keep
+        if only:
+            variants = [v for v in variants if any(tag in v[0] for tag in only.split(","))]
         for (label, impl, terms, mask, store, env) in variants:
             os.environ["ZETT_MMA_MASK"] = str(mask)
             for kk in ("ZETT_L2_HINT_W", "ZETT_L2_HINT_A", "ZETT_STREAM_OUT"):

@@ -663,9 +663,15 @@ int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
   p.H = h->H;
   p.split_fmt = h->gemm.split_fmt;
   const int h4 = h->H / 4;
-  int threads = std::min(256, std::max(32, ((h4 + 31) / 32) * 32));
-  const int grid = static_cast<int>(std::min<long long>(max_rows, 148LL * 16));
-  layernorm_kernel<<<grid, threads, 0, stream>>>(p);
+  if (h4 <= 32 * kLnWarpVec) {  // one warp per row, eight rows per block
+    const int grid = static_cast<int>(std::min<long long>((max_rows + 7) / 8, 148LL * 8));
+    if (h4 <= 32 * 8) layernorm_kernel<true, 8><<<grid, 256, 0, stream>>>(p);
+    else layernorm_kernel<true, kLnWarpVec><<<grid, 256, 0, stream>>>(p);
+  } else {
+    const int threads = std::min(256, std::max(32, ((h4 + 31) / 32) * 32));
+    const int grid = static_cast<int>(std::min<long long>(max_rows, 148LL * 16));
+    layernorm_kernel<false, kLnMaxVec><<<grid, threads, 0, stream>>>(p);
+  }
   ZETT_CUDA(cudaGetLastError());
   ++h->gemm.launches;
   if (debug_enabled() && !p.out_index) {
@@ -676,14 +682,16 @@ int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
 }
 
 int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
-  const long long warps = static_cast<long long>(p.n_rows) * p.n_heads;
+  const int lph = std::min(32, h->dh / 4);  // lanes per head: each lane holds 4 consecutive elements (16-byte loads)
+  const int hpw = 32 / lph;
+  const long long warps = static_cast<long long>(p.n_rows) * ((p.n_heads + hpw - 1) / hpw);
   if (warps == 0) return ZETT_OK;
   const int grid = static_cast<int>((warps + 7) / 8);
-  switch (h->dh / 32) {
-    case 1: attention_kernel<1><<<grid, 256, 0, stream>>>(p); break;
-    case 2: attention_kernel<2><<<grid, 256, 0, stream>>>(p); break;
-    case 4: attention_kernel<4><<<grid, 256, 0, stream>>>(p); break;
-    case 8: attention_kernel<8><<<grid, 256, 0, stream>>>(p); break;
+  switch (h->dh) {
+    case 32: attention_kernel<8, 1><<<grid, 256, 0, stream>>>(p); break;
+    case 64: attention_kernel<16, 1><<<grid, 256, 0, stream>>>(p); break;
+    case 128: attention_kernel<32, 1><<<grid, 256, 0, stream>>>(p); break;
+    case 256: attention_kernel<32, 2><<<grid, 256, 0, stream>>>(p); break;
     default: return fail(ZETT_ERR_UNSUPPORTED, "attention head size must be 32, 64, 128 or 256");
   }
   ZETT_CUDA(cudaGetLastError());

@@ -3,7 +3,7 @@
 //   pack_rows_kernel        surface-form rows -> packed (pad-free) position lists          (modeling_hypernet.py:170-177,190)
 //   gather_rescale_kernel   ids -> source / fallback embedding rows, in_scaler, 16-bit split (modeling_hypernet.py:179-188)
 //   layernorm_kernel        (x [+ residual] [+ type/position embeddings]) -> LayerNorm -> fp32 + split planes
-//   attention_kernel        per (row, head) softmax(q k^T / sqrt(dh) + mask) v over <= S packed positions
+//   attention_kernel        per (row, heads of one warp) softmax(q k^T / sqrt(dh) + mask) v over <= S packed positions
 //   split_planes_kernel     fp32 -> two 16-bit planes (weights at load time)
 //   gemm_simt_kernel        same contract as gemm_tcgen05_kernel, CUDA cores, for checking
 //
@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const Ga
 // compact [n_rows, H] buffers (the pruned last layer reads only those), optionally a dot product with a vector
 // (bias_projection, modeling_hypernet.py:260-265).
 // -------------------------------------------------------------------------------------------------------------------
-constexpr int kLnMaxVec = 8;  // float4 per thread: H <= 4 * 8 * blockDim
+constexpr int kLnMaxVec = 8;    // block per row: float4 per thread, H <= 4 * 8 * blockDim
+constexpr int kLnWarpVec = 16;  // warp per row: float4 per lane, H <= 4 * 16 * 32 = 2048
 
 struct LnParams {
   const float* a;
@@ -335,12 +336,26 @@ __device__ __forceinline__ void store_split4(uint16_t* p0, uint16_t* p1, long lo
   store_operand4(p0, p1, off, v, fmt, is_weight);
 }
 
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// WARP = false: one block per row (H up to 4 * VEC * blockDim), block-wide reductions.
+// WARP = true : one warp per row (H up to 128 * VEC), shuffle reductions only -- rows of a few KB (H <= 2048) are
+//               latency-bound on the two block barriers otherwise (43 % of the HBM roofline at H = 768).
+template <bool WARP, int VEC>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   __shared__ float red[32];
   const int n = p.n_dev ? *p.n_dev : p.n_host;
   const int H4 = p.H >> 2;
-  for (int t = blockIdx.x; t < n; t += gridDim.x) {
-    float4 v[kLnMaxVec];
+  const int lane_in_row = WARP ? (threadIdx.x & 31) : threadIdx.x;
+  const int row_threads = WARP ? 32 : blockDim.x;
+  const int rows_per_block = WARP ? (blockDim.x >> 5) : 1;
+  auto row_sum = [&](float v) { return WARP ? warp_sum(v) : block_sum(v, red); };
+  for (int t = blockIdx.x * rows_per_block + (WARP ? (threadIdx.x >> 5) : 0); t < n; t += gridDim.x * rows_per_block) {
+    float4 v[VEC];
     const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(p.in_index ? __ldg(p.in_index + t) : t) * p.lda);
     const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res + static_cast<long long>(t) * p.H) : nullptr;
     const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) : nullptr;
@@ -351,8 +366,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kLnMaxVec; ++c) {
-      const int i = threadIdx.x + c * blockDim.x;
+    for (int c = 0; c < VEC; ++c) {
+      const int i = lane_in_row + c * row_threads;
       if (i < H4) {
         float4 x = a4[i];
         if (r4) { const float4 y = r4[i]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
@@ -362,17 +377,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
         s += (x.x + x.y) + (x.z + x.w);
       }
     }
-    const float mean = block_sum(s, red) / static_cast<float>(p.H);
+    const float mean = row_sum(s) / static_cast<float>(p.H);
     float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < kLnMaxVec; ++c) {
-      const int i = threadIdx.x + c * blockDim.x;
+    for (int c = 0; c < VEC; ++c) {
+      const int i = lane_in_row + c * row_threads;
       if (i < H4) {
         const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
         q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
       }
     }
-    const float var = block_sum(q, red) / static_cast<float>(p.H);
+    const float var = row_sum(q) / static_cast<float>(p.H);
     const float rstd = 1.0f / sqrtf(var + p.eps);
 
     const long long o = static_cast<long long>(p.out_index ? __ldg(p.out_index + t) : t) * p.H;
@@ -386,8 +401,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     const float4* b4 = reinterpret_cast<const float4*>(p.beta);
     const float4* w4 = p.dot_w ? reinterpret_cast<const float4*>(p.dot_w) : nullptr;
 #pragma unroll
-    for (int c = 0; c < kLnMaxVec; ++c) {
-      const int i = threadIdx.x + c * blockDim.x;
+    for (int c = 0; c < VEC; ++c) {
+      const int i = lane_in_row + c * row_threads;
       if (i < H4) {
         const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
         float4 y;
@@ -408,18 +423,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       }
     }
     if (w4) {
-      const float d = block_sum(dot, red);
-      if (threadIdx.x == 0) p.dot_out[static_cast<long long>(t) * p.dot_ld] = d + __ldg(p.dot_b);
+      const float d = row_sum(dot);
+      if (lane_in_row == 0) p.dot_out[static_cast<long long>(t) * p.dot_ld] = d + __ldg(p.dot_b);
     }
   }
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// Attention over the <= S packed positions of one row: one warp per (row, head); lane l holds elements l, l + 32, ...
-// of the head vectors (coalesced 128-byte reads), dot products reduce with warp shuffles, softmax is an online
-// running max / sum in fp32 (HF eager attention: scores * dh^-0.5 + additive mask, softmax, @ V).
-// A row without any valid key gets uniform weights over all of its positions (what finfo.min + softmax yields).
-// row0_only: only the first position of each row is a query (pruned last layer); q and out are then indexed by row.
+// Attention over the <= S packed positions of one row.  LPH lanes hold one head (4 * VPL consecutive elements each,
+// 16-byte loads), so a warp serves 32 / LPH heads of a row at once; dot products reduce with shuffles inside the LPH
+// lanes, softmax is an online running max / sum in fp32 (HF eager attention: scores * dh^-0.5 + additive mask,
+// softmax, @ V).  A row without any valid key gets uniform weights over all of its positions (what finfo.min +
+// softmax yields).  row0_only: only the first position of each row is a query (pruned last layer); q and out are
+// then indexed by row.  qkv_index: q / k / v rows are read through an index (first layer on distinct pairs).
 // -------------------------------------------------------------------------------------------------------------------
 struct AttnParams {
   const float* q; long long ldq;
@@ -437,54 +453,70 @@ struct AttnParams {
   int split_fmt;
 };
 
-template <int DPL>
+template <int LPH, int VPL>
 __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
+  constexpr int HPW = 32 / LPH;  // heads per warp
   const int lane = threadIdx.x & 31;
+  const int groups = (p.n_heads + HPW - 1) / HPW;
   const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wid >= static_cast<long long>(p.n_rows) * p.n_heads) return;
-  const int r = static_cast<int>(wid / p.n_heads);
-  const int h = static_cast<int>(wid % p.n_heads);
+  if (wid >= static_cast<long long>(p.n_rows) * groups) return;
+  const int r = static_cast<int>(wid / groups);
+  const int h = static_cast<int>(wid % groups) * HPW + lane / LPH;
+  const bool head_ok = h < p.n_heads;               // lanes of a missing head still take part in the shuffles
+  const int hoff = (head_ok ? h : 0) * p.dh + (lane % LPH) * 4;
   const int t0 = __ldg(p.row_start + r), t1 = __ldg(p.row_start + r + 1);
   const int n = t1 - t0;
-  const int hoff = h * p.dh + lane;
   uint32_t valid_mask = 0;
   for (int j = 0; j < n; ++j) valid_mask |= (__ldg(p.valid + t0 + j) != 0 ? 1u : 0u) << j;
   const bool any_valid = valid_mask != 0;
   const int n_q = p.row0_only ? 1 : n;
-  // K and V are streamed per query (L1-resident re-reads); keeping them in registers was measured slower: the kernel is
-  // latency-bound and the register footprint cost more occupancy than the re-reads cost bandwidth
+  // K and V are streamed per query (L1-resident re-reads); keeping them in registers was measured slower
   for (int i = 0; i < n_q; ++i) {
     const long long qi = p.row0_only ? r : (p.qkv_index ? __ldg(p.qkv_index + t0 + i) : (t0 + i));
-    float qv[DPL];
+    float4 qv[VPL];
 #pragma unroll
-    for (int d = 0; d < DPL; ++d) qv[d] = __ldg(p.q + qi * p.ldq + hoff + 32 * d);
-    float m = -INFINITY, l = 0.f, acc[DPL];
+    for (int d = 0; d < VPL; ++d) qv[d] = __ldg(reinterpret_cast<const float4*>(p.q + qi * p.ldq + hoff + 4 * LPH * d));
+    float m = -INFINITY, l = 0.f;
+    float4 acc[VPL];
 #pragma unroll
-    for (int d = 0; d < DPL; ++d) acc[d] = 0.f;
+    for (int d = 0; d < VPL; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < n; ++j) {
       if (any_valid && !((valid_mask >> j) & 1u)) continue;  // masked key: weight exactly 0
+      const long long kvj = p.qkv_index ? __ldg(p.qkv_index + t0 + j) : (t0 + j);
       float s = 0.f;
       if (any_valid) {
-        const float* kj = p.k + static_cast<long long>(p.qkv_index ? __ldg(p.qkv_index + t0 + j) : (t0 + j)) * p.ldk + hoff;
+        const float* kj = p.k + kvj * p.ldk + hoff;
 #pragma unroll
-        for (int d = 0; d < DPL; ++d) s += qv[d] * __ldg(kj + 32 * d);
+        for (int d = 0; d < VPL; ++d) {
+          const float4 kk = __ldg(reinterpret_cast<const float4*>(kj + 4 * LPH * d));
+          s += (qv[d].x * kk.x + qv[d].y * kk.y) + (qv[d].z * kk.z + qv[d].w * kk.w);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        for (int o = LPH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
         s *= p.scale;
       }
       const float m_new = fmaxf(m, s);
       const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
       const float w = expf(s - m_new);
       l = l * corr + w;
-      const float* vj = p.v + static_cast<long long>(p.qkv_index ? __ldg(p.qkv_index + t0 + j) : (t0 + j)) * p.ldv + hoff;
+      const float* vj = p.v + kvj * p.ldv + hoff;
 #pragma unroll
-      for (int d = 0; d < DPL; ++d) acc[d] = acc[d] * corr + w * __ldg(vj + 32 * d);
+      for (int d = 0; d < VPL; ++d) {
+        const float4 vv = __ldg(reinterpret_cast<const float4*>(vj + 4 * LPH * d));
+        acc[d].x = acc[d].x * corr + w * vv.x; acc[d].y = acc[d].y * corr + w * vv.y;
+        acc[d].z = acc[d].z * corr + w * vv.z; acc[d].w = acc[d].w * corr + w * vv.w;
+      }
       m = m_new;
     }
     const float inv = 1.0f / l;
     const long long oi = (p.row0_only ? r : (t0 + i)) * p.ld_out + hoff;
+    if (head_ok) {
 #pragma unroll
-    for (int d = 0; d < DPL; ++d) store_operand1(p.out_p0, p.out_p1, oi + 32 * d, acc[d] * inv, p.split_fmt);
+      for (int d = 0; d < VPL; ++d) {
+        const float y[4] = {acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv};
+        store_operand4(p.out_p0, p.out_p1, oi + 4 * LPH * d, y, p.split_fmt, false);
+      }
+    }
   }
 }
 
