@@ -294,7 +294,15 @@ struct GemmEngine {
     GemmShape s{};
     s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
     s.block_n = pick_block_n(g.n);
-    s.n_halves = (impl == 5 && s.block_n == 256 && g.n % 512 == 0) ? 2 : 1;
+    s.n_halves = 1;
+    if (impl == 5 && s.block_n == 256 && g.n % 512 == 0 && g.k >= 4096) {
+      // 256 x 512 tiles pay when the main loop is long enough to dwarf the exposed epilogue (K >= 4096) and the coarser
+      // tiles still fill whole waves of CTA pairs (a data-dependent M is taken at half its bound, the usual fill)
+      const long long m_est = g.m_dev ? std::max(1, g.m_host / 2) : g.m_host;
+      const long long tiles = ((m_est + 255) / 256) * (g.n / 512), pairs = std::max(1, dev.num_sms / 2);
+      const long long waves = (tiles + pairs - 1) / pairs;
+      if (tiles * 10 >= waves * pairs * 9) s.n_halves = 2;
+    }
     s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0; s.mma_mask = mma_mask;
     s.hint_a = hint_a; s.hint_b = hint_b;
     const int load_n = s.block_n / cg;
