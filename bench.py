@@ -197,12 +197,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def profile_of_largest_gemm(config, fmt_tag):
+def profile_of_largest_gemm(config, fmt_tag, impl):
     """DRAM bytes (read + write) of one launch of the largest GEMM of the step, from the committed ncu summary."""
     if config != "mistral":
         return None
-    for rnd in ("r1",):
-        path = os.path.join(ROOT, "profiles", "gemm_tcgen05_%s_%s_53248x12288x4096.csv" % (rnd, fmt_tag))
+    tags = ([fmt_tag + "_wide"] if impl == 5 else []) + [fmt_tag]  # 256 x 512 pair tiles have their own capture
+    for path in [os.path.join(ROOT, "profiles", "gemm_tcgen05_%s_%s_53248x12288x4096.csv" % (rnd, tag)) for rnd in ("r1",) for tag in tags]:
         if not os.path.exists(path):
             continue
         vals = {}
@@ -365,7 +365,7 @@ def run_ours(args):
                      "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": st["gemm_launches"],
                      "mma_issue_tflops_f16_equivalent": (achieved * fmt[2]) if achieved else None},
     }
-    prof = profile_of_largest_gemm(args.config, fmt[1])
+    prof = profile_of_largest_gemm(args.config, fmt[1], int(st["gemm_impl"]))
     if prof:
         line["roofline"]["traffic"] = prof["traffic"]
         line["roofline"]["profile"] = prof["note"]
