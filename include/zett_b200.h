@@ -178,6 +178,16 @@ int zett_surface_forms(const zett_tok* t, const char* const* tokens, int64_t v, 
                        int32_t maxlen, int32_t pad_id, int64_t padding, int32_t* out, int64_t* n_truncated,
                        int n_threads);
 
+/* Same result from ONE buffer: `tokens_blob` holds the v token strings back to back, each terminated by a NUL byte
+ * (so `"\0".join(tokens)` plus the terminator every C string carries); `special_blob` / `special_token_ids` list the hn
+ * tokenizer's special tokens (hn_tokenizer.all_special_tokens, zett/utils.py:671-673) the same way, n_special of them,
+ * and the match against them happens inside.  This is the entry point a binding should prefer for a whole vocabulary:
+ * building an array of 50k char* in the host language costs more than the retokenisation itself. */
+int zett_surface_forms_blob(const zett_tok* t, const char* tokens_blob, int64_t blob_bytes, int64_t v,
+                            const char* special_blob, int64_t special_bytes, const int32_t* special_token_ids,
+                            int64_t n_special, int32_t maxlen, int32_t pad_id, int64_t padding, int32_t* out,
+                            int64_t* n_truncated, int n_threads);
+
 void zett_tok_destroy(zett_tok* t);
 
 #ifdef __cplusplus

@@ -122,3 +122,26 @@ def test_tokenizer_object_input():
     got, _ = get_surface_form_matrix(target, 7, hn)
     want, _ = ro.surface_form_matrix_hf(target.convert_ids_to_tokens(range(len(target))), 7, hn)
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", INT_CASES)
+def test_blob_entry_point_equals_pointer_array(golden_dir, case):
+    """zett_surface_forms_blob (one NUL-separated buffer, special tokens matched natively) == zett_surface_forms (char*
+    array, per-token special ids) == the reference-minted golden; an embedded NUL falls back to the array path."""
+    g = np.load(os.path.join(golden_dir, f"surface_forms_{case}.npz"))
+    spec, tokens = json.loads(str(g["spec"])), json.loads(str(g["tokens"]))
+    model = native_model(spec)
+    out, n_trunc = model.surface_forms(tokens, int(g["maxlen"]), spec["pad_token_id"], None, int(g["padding"]),
+                                       special_tokens=spec["special_tokens"])
+    np.testing.assert_array_equal(out, g["matrix"])
+    assert n_trunc == int(g["n_truncated"])
+    # ragged edges: no tokens, one empty token, empty tokens at both ends, no special tokens at all
+    for toks in ([], [""], ["", tokens[1], ""], tokens[:1]):
+        sp = np.array([spec["special_tokens"].get(t, -1) for t in toks], dtype=np.int32)
+        a, na = model.surface_forms(toks, 5, spec["pad_token_id"], sp)
+        b, nb = model.surface_forms(toks, 5, spec["pad_token_id"], special_tokens=spec["special_tokens"])
+        c, nc = model.surface_forms(toks, 5, spec["pad_token_id"], special_tokens={})
+        np.testing.assert_array_equal(a, b)
+        assert na == nb and a.shape == (len(toks), 5)
+        if not any(t in spec["special_tokens"] for t in toks):
+            np.testing.assert_array_equal(a, c)

@@ -98,6 +98,8 @@ SIGNATURES = {
     "zett_tok_tokenize": (c_int64, [c_void_p, c_char_p, POINTER(c_int32), c_int64]),
     "zett_surface_forms": (c_int, [c_void_p, POINTER(c_char_p), c_int64, POINTER(c_int32), c_int32, c_int32, c_int64,
                                    POINTER(c_int32), POINTER(c_int64), c_int]),
+    "zett_surface_forms_blob": (c_int, [c_void_p, c_char_p, c_int64, c_int64, c_char_p, c_int64, POINTER(c_int32), c_int64,
+                                        c_int32, c_int32, c_int64, POINTER(c_int32), POINTER(c_int64), c_int]),
     "zett_tok_destroy": (None, [c_void_p]),
 }
 

@@ -175,8 +175,14 @@ struct zett_tok {
     out.clear();
     if (n == 0) return ZETT_OK;
     const double unk_score = min_score - 10.0;
-    std::vector<double> best(n + 1, 0.0);
-    std::vector<int32_t> start(n + 1, -1), node_id(n + 1, 0);
+    // per-thread scratch: a vocabulary is ~50k short strings, the allocations would cost as much as the search
+    thread_local std::vector<double> best;
+    thread_local std::vector<int32_t> start, node_id;
+    thread_local std::vector<std::pair<int32_t, int32_t>> spans;  // [start, end)
+    best.assign(n + 1, 0.0);
+    start.assign(n + 1, -1);
+    node_id.assign(n + 1, 0);
+    spans.clear();
     size_t pos = 0;
     while (pos < n) {
       const double here = best[pos];
@@ -206,7 +212,6 @@ struct zett_tok {
       pos += mblen;
     }
     // backtrack, fusing consecutive unk nodes; pieces come out right-to-left
-    std::vector<std::pair<int32_t, int32_t>> spans;  // [start, end)
     int32_t pend_start = -1, pend_end = -1;
     size_t end = n;
     while (end > 0) {
@@ -247,9 +252,10 @@ struct zett_tok {
       const int32_t tid = trie.find(w.data(), w.size());
       if (tid >= 0) { out.push_back(tid); return ZETT_OK; }
     }
-    std::vector<int32_t> c;
+    thread_local std::vector<int32_t> c;
+    thread_local std::string sym;
+    c.clear();
     int32_t unk = -1;
-    std::string sym;
     for (size_t i = 0; i < w.size();) {
       const size_t len = std::min<size_t>(utf8_len(static_cast<unsigned char>(w[i])), w.size() - i);
       const bool first = i == 0, last = i + len >= w.size();
@@ -280,8 +286,11 @@ struct zett_tok {
     if (unk >= 0) c.push_back(unk);
     const int n = static_cast<int>(c.size());
     if (n == 0) return ZETT_OK;
-    std::vector<char> alive(n, 1);
-    std::vector<int> prev(n), nxt(n);
+    thread_local std::vector<char> alive;
+    thread_local std::vector<int> prev, nxt;
+    alive.assign(n, 1);
+    prev.resize(n);
+    nxt.resize(n);
     for (int i = 0; i < n; ++i) { prev[i] = i - 1; nxt[i] = (i + 1 < n) ? i + 1 : -1; }
     struct Item { int32_t rank; int pos; int32_t new_id; };
     auto cmp = [](const Item& a, const Item& b) {
@@ -395,9 +404,20 @@ int64_t zett_tok_tokenize(const zett_tok* t, const char* token, int32_t* out_ids
   return static_cast<int64_t>(ids.size());
 }
 
-int zett_surface_forms(const zett_tok* t, const char* const* tokens, int64_t v, const int32_t* special_ids, int32_t maxlen,
-                       int32_t pad_id, int64_t padding, int32_t* out, int64_t* n_truncated, int n_threads) {
+}  // extern "C"
+
+namespace {
+
+using SpecialMap = std::unordered_map<std::string, int32_t>;
+
+// shared body of the two entry points: special tokens are given per token (special_ids) or as a map matched in the workers
+int surface_forms_impl(const zett_tok* t, const char* const* tokens, int64_t v, const int32_t* special_ids,
+                       const SpecialMap* special_map, int32_t maxlen, int32_t pad_id, int64_t padding, int32_t* out,
+                       int64_t* n_truncated, int n_threads) {
   if (!t || (!tokens && v > 0) || !out || v < 0 || maxlen <= 0 || padding < 0) return tok_fail(ZETT_ERR_INVALID, "bad argument");
+  size_t max_special = 0;
+  if (special_map)
+    for (const auto& kv : *special_map) max_special = std::max(max_special, kv.first.size());
   std::fill(out, out + (v + padding) * maxlen, pad_id);
   int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
   nt = std::max(1, std::min<int>(nt, static_cast<int>(std::max<int64_t>(1, v / 256))));
@@ -415,6 +435,10 @@ int zett_surface_forms(const zett_tok* t, const char* const* tokens, int64_t v, 
         continue;
       }
       s.assign(tokens[i]);
+      if (special_map && s.size() <= max_special) {
+        auto it = special_map->find(s);
+        if (it != special_map->end()) { out[i * maxlen] = it->second; continue; }
+      }
       int rc = ZETT_OK;
       for (size_t p = 0; p < s.size();) {  // bytes([CHARS_TO_BYTES[c] for c in token]) raises KeyError (utils.py:675)
         const int len = std::min<size_t>(utf8_len(static_cast<unsigned char>(s[p])), s.size() - p);
@@ -454,6 +478,45 @@ int zett_surface_forms(const zett_tok* t, const char* const* tokens, int64_t v, 
   }
   if (n_truncated) *n_truncated = truncated.load();
   return ZETT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zett_surface_forms(const zett_tok* t, const char* const* tokens, int64_t v, const int32_t* special_ids, int32_t maxlen,
+                       int32_t pad_id, int64_t padding, int32_t* out, int64_t* n_truncated, int n_threads) {
+  return surface_forms_impl(t, tokens, v, special_ids, nullptr, maxlen, pad_id, padding, out, n_truncated, n_threads);
+}
+
+int zett_surface_forms_blob(const zett_tok* t, const char* tokens_blob, int64_t blob_bytes, int64_t v,
+                            const char* special_blob, int64_t special_bytes, const int32_t* special_token_ids,
+                            int64_t n_special, int32_t maxlen, int32_t pad_id, int64_t padding, int32_t* out,
+                            int64_t* n_truncated, int n_threads) {
+  if (!t || v < 0 || blob_bytes < 0 || (!tokens_blob && v > 0) || n_special < 0 || (n_special > 0 && (!special_blob || !special_token_ids)))
+    return tok_fail(ZETT_ERR_INVALID, "bad argument");
+  // token starts: one pass over the buffer (a few hundred KB for a whole vocabulary)
+  std::vector<const char*> ptrs(static_cast<size_t>(v));
+  const char* p = tokens_blob;
+  const char* end = tokens_blob + blob_bytes;
+  for (int64_t i = 0; i < v; ++i) {
+    if (p > end) return tok_fail(ZETT_ERR_INVALID, "tokens_blob holds fewer than v NUL-terminated strings");
+    ptrs[static_cast<size_t>(i)] = p;
+    const void* z = p < end ? memchr(p, 0, static_cast<size_t>(end - p)) : nullptr;
+    p = z ? static_cast<const char*>(z) + 1 : end + 1;  // the last string may rely on the buffer's own terminator
+  }
+  SpecialMap special;
+  const char* q = special_blob;
+  const char* qend = special_blob + special_bytes;
+  for (int64_t i = 0; i < n_special; ++i) {
+    if (q > qend) return tok_fail(ZETT_ERR_INVALID, "special_blob holds fewer than n_special strings");
+    const void* z = q < qend ? memchr(q, 0, static_cast<size_t>(qend - q)) : nullptr;
+    const char* stop = z ? static_cast<const char*>(z) : qend;
+    special.emplace(std::string(q, stop), special_token_ids[i]);  // first occurrence wins, like list.index
+    q = stop + 1;
+  }
+  return surface_forms_impl(t, ptrs.data(), v, nullptr, special.empty() ? nullptr : &special, maxlen, pad_id, padding, out,
+                            n_truncated, n_threads);
 }
 
 void zett_tok_destroy(zett_tok* t) { delete t; }

@@ -84,17 +84,31 @@ class NativeTokenizerModel:
         return list(buf[:n])
 
     def surface_forms(self, tokens: Sequence[str], maxlen: int, pad_id: int, special_ids: Optional[np.ndarray] = None,
-                      padding: int = 0, n_threads: int = 0):
+                      padding: int = 0, n_threads: int = 0, special_tokens: Optional[Dict[str, int]] = None):
+        """``special_ids`` (per token, -1 = ordinary) or ``special_tokens`` ({token: id}, matched natively) mark the hn
+        tokenizer's special tokens.  The vocabulary crosses the ABI as ONE NUL-separated buffer: marshalling 50k strings
+        into a ``char*`` array costs twice the retokenisation itself."""
         v = len(tokens)
-        arr = (ctypes.c_char_p * max(v, 1))(*[t.encode("utf-8") for t in tokens])
         out = np.empty((v + padding, maxlen), dtype=np.int32)
+        out_p = out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
         n_trunc = ctypes.c_int64(0)
+        blob = "\0".join(tokens).encode("utf-8") if special_ids is None else None
+        if blob is not None and blob.count(b"\0") == max(v - 1, 0):  # no token holds a NUL itself
+            sp_tokens = list(special_tokens or {})
+            sp_blob = "\0".join(sp_tokens).encode("utf-8")
+            sp_ids = (ctypes.c_int32 * max(len(sp_tokens), 1))(*[int(special_tokens[t]) for t in sp_tokens])
+            _lib.check(self.lib.zett_surface_forms_blob(self.handle, blob, len(blob), v, sp_blob, len(sp_blob), sp_ids,
+                                                        len(sp_tokens), maxlen, pad_id, padding, out_p, ctypes.byref(n_trunc),
+                                                        n_threads))
+            return out, int(n_trunc.value)
+        if special_ids is None and special_tokens:
+            special_ids = np.fromiter((special_tokens.get(t, -1) for t in tokens), dtype=np.int32, count=v)
+        arr = (ctypes.c_char_p * max(v, 1))(*[t.encode("utf-8") for t in tokens])
         sp = None
         if special_ids is not None:
             special_ids = np.ascontiguousarray(special_ids, dtype=np.int32)
             sp = special_ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
-        _lib.check(self.lib.zett_surface_forms(self.handle, arr, v, sp, maxlen, pad_id, padding,
-                                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(n_trunc),
+        _lib.check(self.lib.zett_surface_forms(self.handle, arr, v, sp, maxlen, pad_id, padding, out_p, ctypes.byref(n_trunc),
                                                n_threads))
         return out, int(n_trunc.value)
 
@@ -137,14 +151,9 @@ def get_surface_form_matrix(tokenizer_or_tokens, maxlen, tokenizer_to_use=None, 
         raise AttributeError("'NoneType' object has no attribute 'all_special_tokens'")
     if type(tokenizer_to_use).__name__ == "ByT5Tokenizer":
         raise NotImplementedError("ByT5 hn tokenizers are not supported by the native retokenizer")
-    special = list(tokenizer_to_use.all_special_tokens)
-    special_map = {t: int(tokenizer_to_use.convert_tokens_to_ids(t)) for t in special}
-    special_ids = np.full(len(tokens), -1, dtype=np.int32)
-    if special_map:
-        for i, t in enumerate(tokens):
-            sid = special_map.get(t)
-            if sid is not None:
-                special_ids[i] = sid
+    special_map = {}
+    for t in tokenizer_to_use.all_special_tokens:  # first occurrence wins, like `token in all_special_tokens`
+        special_map.setdefault(t, int(tokenizer_to_use.convert_tokens_to_ids(t)))
     model = native_model_for(tokenizer_to_use)
-    return model.surface_forms(tokens, int(maxlen), int(tokenizer_to_use.pad_token_id), special_ids, int(padding),
-                               n_threads)
+    return model.surface_forms(tokens, int(maxlen), int(tokenizer_to_use.pad_token_id), None, int(padding), n_threads,
+                               special_tokens=special_map)

@@ -256,8 +256,7 @@ class TokenPipeline:
         for lo in range(0, n, self.rows_per_pass):
             hi = min(n, lo + self.rows_per_pass)
             chunk = tokens[lo:hi]
-            special_ids = np.fromiter((self.special.get(t, -1) for t in chunk), dtype=np.int32, count=hi - lo)
-            sf, nt = self.tok_model.surface_forms(chunk, cfg.hn_surface_maxlen, self.pad_id, special_ids)  # host
+            sf, nt = self.tok_model.surface_forms(chunk, cfg.hn_surface_maxlen, self.pad_id, special_tokens=self.special)  # host
             n_trunc += nt
             self.sf_pinned[lo:hi].numpy()[...] = sf
             self.sf_dev[lo:hi].copy_(self.sf_pinned[lo:hi], non_blocking=True)                              # H2D
