@@ -31,6 +31,24 @@ def split2(x, dt):
     return hi, r16(x - hi, dt)
 
 
+def q_e5m2(x):
+    return x.to(torch.float8_e5m2).to(torch.float32)
+
+
+_E2M1 = torch.tensor([0, 0.5, 1, 1.5, 2, 3, 4, 6.0])
+
+
+def q_mxfp4(x, block=32):
+    """OCP MXFP4: e2m1 values with one power-of-two (ue8m0) scale per block of 32 K-elements."""
+    sh = x.shape
+    xb = x.reshape(-1, sh[-1] // block, block)
+    amax = xb.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30)
+    s = torch.exp2(torch.floor(torch.log2(amax)) - 2)
+    y = (xb / s).clamp(-6, 6)
+    q = _E2M1[(y.abs().unsqueeze(-1) - _E2M1).abs().argmin(dim=-1)] * torch.sign(y)
+    return (q * s).reshape(sh)
+
+
 class Shim:
     """Stands in for torch.nn.functional inside the oracle module; only `linear` changes."""
 
@@ -54,6 +72,13 @@ class Shim:
             return F.linear(r16(x, torch.float16), r16(w, torch.float16), b)
         if mode == "bf16":
             return F.linear(r16(x, torch.bfloat16), r16(w, torch.bfloat16), b)
+        if mode in ("f16f8", "f16f4"):  # fp16 main term + two first-order correction terms in fp8 (e5m2) or block-scaled fp4
+            x0, w0 = r16(x, torch.float16), r16(w, torch.float16)
+            xl, wl = x - x0, w - w0
+            y = F.linear(x0, w0, b)
+            if mode == "f16f8":  # the 2^+-6 factors of zett_b200/csrc/epilogue.cuh
+                return y + F.linear(q_e5m2(xl * 64), q_e5m2(w / 64)) + F.linear(q_e5m2(x / 64), q_e5m2(wl * 64))
+            return y + F.linear(q_mxfp4(xl), q_mxfp4(w)) + F.linear(q_mxfp4(x), q_mxfp4(wl))
         if mode == "bf16x3":
             a0, a1 = split2(x, torch.bfloat16)
             w0, w1 = split2(w, torch.bfloat16)
@@ -99,7 +124,9 @@ def main():
     # GEMM call order in the oracle: 0 in_proj0, 1-2 in_proj1, per layer l: 3+6l.. q k v o inter out, 21-23 head_in, 24-26 head_out
     enc = set(range(3, 21))
     policies = {
-        "bf16x3 (default)": lambda i, s: "bf16x3",
+        "f16 + 2 x e5m2 (default)": lambda i, s: "f16f8",
+        "bf16x3 (split_terms = 3)": lambda i, s: "bf16x3",
+        "f16 + 2 x mxfp4 (not built)": lambda i, s: "f16f4",
         "a16 everywhere": lambda i, s: "a16",
         "w16 everywhere": lambda i, s: "w16",
         "f16 single pass": lambda i, s: "f16",
