@@ -6,10 +6,10 @@
 //    ~fp32 operand precision (the 1e-3 parity budget rules out single-pass bf16); or fp16 + two e5m2
 //    correction planes (f8): one kind::f16 MMA + two kind::f8f6f4 MMAs per k-step.
 //  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}; 128-byte swizzle: 16-bit rows of BLOCK_K = 64, or the two
-//    fp8 planes of a k-block interleaved in one line), warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias / GELU / residual /
-//    column affine -> fp32 and/or operand planes for the next GEMM).
-//  * accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the main loop of
-//    tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
+//    fp8 planes of a k-block interleaved in one line), warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
+//    (tcgen05.ld -> bias / GELU / residual / column affine -> fp32 and/or operand planes for the next GEMM).
+//  * n_halves == 1: accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+//    main loop of tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
 //  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the B tile; the
 //    leader alone arrives on the full barrier (expecting both CTAs' bytes), issues the MMAs and multicasts the commits.
 //  * eight epilogue warps, two per TMEM lane quarter: the two groups of four take alternate 32-column chunks of one
@@ -17,11 +17,11 @@
 //    conversion, 16-byte stores -- and with K = 768 it is as long as the main loop of a tile).
 //  * CP == 2 puts two such pairs in one cluster of four CTAs working on vertically adjacent 256-row tiles of the same
 //    N tile: every CTA fetches only HALF of its pair's share of the W tile and TMA-multicasts it to the CTA holding the
-//    same share in the other pair (.multicast::cluster), so a cluster moves 4 A blocks + 2 W blocks through L2 -> SM
-//    instead of 4 + 4.  The kernel is bound by L2 slice throughput (~6.5 KB/clk chip-wide), so the
-//    25 % fewer bytes are what lets the formats with fewer MMAs per byte reach the tensor pipe.  A smem stage of a CTA is
-//    then written by two CTAs, so every empty barrier counts one tcgen05.commit from EACH pair leader (multicast to all
-//    four CTAs); the full barriers stay per pair.
+//    same share in the other pair (.multicast::cluster), so a cluster reads 4 A blocks + 2 W blocks from the L2 slices
+//    instead of 4 + 4.  Measured: -19 % L2 slice reads, -16 % DRAM reads, but the bytes ARRIVING at
+//    each SM are unchanged and only 33 clusters of four fit the 148 SMs, so it ends within 2 % of plain pairs; kept as
+//    gemm_impl 4, not the default.  A smem stage of a CTA is then written by two CTAs, so every empty barrier counts one
+//    tcgen05.commit from EACH pair leader (multicast to all four CTAs); the full barriers stay per pair.
 //  * n_halves == 2 (gemm_impl 5) widens the tile of a CTA pair to 256 x 512: both accumulators of TMEM hold the two N halves
 //    of ONE tile, every k-block of A is fetched once for 512 columns (25 % fewer operand bytes per FLOP, the largest item of
 //    the kernel's energy budget after the MMAs), at the price of two 96 KB smem stages instead of
