@@ -1,10 +1,11 @@
 // The non-GEMM kernels of the hypernetwork forward, plus the SIMT fp32 GEMM used as the on-device checker.
 //
-//   pack_rows_kernel        surface-form rows -> packed (pad-free) position lists          (modeling_hypernet.py:170-177,190)
+//   pack_*_kernel (five)    surface-form rows -> packed (pad-free) position lists, distinct ids / (id, position) pairs
+//                           (modeling_hypernet.py:170-177,190)
 //   gather_rescale_kernel   ids -> source / fallback embedding rows, in_scaler, 16-bit split (modeling_hypernet.py:179-188)
 //   layernorm_kernel        (x [+ residual] [+ type/position embeddings]) -> LayerNorm -> fp32 + split planes
 //   attention_kernel        per (row, heads of one warp) softmax(q k^T / sqrt(dh) + mask) v over <= S packed positions
-//   split_planes_kernel     fp32 -> two 16-bit planes (weights at load time)
+//   split_planes_kernel     fp32 -> operand planes of the GEMM engine (weights at load time)
 //   gemm_simt_kernel        same contract as gemm_tcgen05_kernel, CUDA cores, for checking
 //
 // Packing.  A surface-form row holds L ids, most of them pad (mean non-pad length ~2.9 of 7 on the benchmark
