@@ -137,6 +137,55 @@ class ByteTrie {
   std::vector<int32_t> value_;
 };
 
+// (left id, right id) -> (rank, merged id): open addressing, one probe on average -- the BPE loop does ~2 look-ups per
+// symbol and std::unordered_map made them the largest item of a retokenisation
+class PairMap {
+ public:
+  void reserve(size_t n) {
+    size_t cap = 16;
+    while (cap < n * 2) cap <<= 1;
+    keys_.assign(cap, kEmpty);
+    vals_.assign(cap, {0, 0});
+    mask_ = cap - 1;
+    used_ = 0;
+  }
+  void set(uint64_t key, std::pair<int32_t, int32_t> v) {  // later duplicates win
+    if ((used_ + 1) * 2 > keys_.size()) grow();
+    size_t i = hash(key) & mask_;
+    while (keys_[i] != kEmpty && keys_[i] != key) i = (i + 1) & mask_;
+    if (keys_[i] == kEmpty) { keys_[i] = key; ++used_; }
+    vals_[i] = v;
+  }
+  inline const std::pair<int32_t, int32_t>* find(uint64_t key) const {
+    size_t i = hash(key) & mask_;
+    while (true) {
+      const uint64_t k = keys_[i];
+      if (k == key) return &vals_[i];
+      if (k == kEmpty) return nullptr;
+      i = (i + 1) & mask_;
+    }
+  }
+
+ private:
+  static constexpr uint64_t kEmpty = ~0ull;  // no pair of non-negative ids packs to this
+  static inline uint64_t hash(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+  }
+  void grow() {
+    std::vector<uint64_t> ok;
+    std::vector<std::pair<int32_t, int32_t>> ov;
+    ok.swap(keys_);
+    ov.swap(vals_);
+    reserve(ok.size());
+    for (size_t i = 0; i < ok.size(); ++i)
+      if (ok[i] != kEmpty) set(ok[i], ov[i]);
+  }
+  std::vector<uint64_t> keys_ = std::vector<uint64_t>(16, kEmpty);
+  std::vector<std::pair<int32_t, int32_t>> vals_ = std::vector<std::pair<int32_t, int32_t>>(16, {0, 0});
+  size_t mask_ = 15, used_ = 0;
+};
+
 struct TokError {
   int code = 0;
 };
@@ -155,7 +204,7 @@ struct zett_tok {
   std::vector<double> scores;
   double min_score = std::numeric_limits<double>::infinity();
   // bpe
-  std::unordered_map<uint64_t, std::pair<int32_t, int32_t>> merges;  // (a << 32 | b) -> (rank, new id)
+  PairMap merges;  // (a << 32 | b) -> (rank, new id)
   std::string prefix, suffix;
   bool has_prefix = false, has_suffix = false, fuse_unk = false, ignore_merges = false;
 
@@ -300,8 +349,7 @@ struct zett_tok {
     };
     std::priority_queue<Item, std::vector<Item>, decltype(cmp)> heap(cmp);
     auto lookup = [&](int32_t a, int32_t b) -> const std::pair<int32_t, int32_t>* {
-      auto it = merges.find((static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b));
-      return it == merges.end() ? nullptr : &it->second;
+      return merges.find((static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b));
     };
     for (int i = 0; i + 1 < n; ++i)
       if (auto* m = lookup(c[i], c[i + 1])) heap.push({m->first, i, m->second});
@@ -377,7 +425,7 @@ int zett_tok_create_bpe(const char* const* vocab, int64_t n, const int32_t* merg
   for (int64_t i = 0; i < n; ++i) total += strlen(vocab[i]);
   t->trie.reserve_edges(total);
   for (int64_t i = 0; i < n; ++i) t->trie.insert(vocab[i], static_cast<int32_t>(i));
-  t->merges.reserve(static_cast<size_t>(m) * 2);
+  t->merges.reserve(static_cast<size_t>(m));
   const size_t plen = t->prefix.size();
   for (int64_t r = 0; r < m; ++r) {
     const int32_t a = merges[2 * r], b = merges[2 * r + 1];
@@ -388,7 +436,7 @@ int zett_tok_create_bpe(const char* const* vocab, int64_t n, const int32_t* merg
     joined.append(bs + std::min(plen, bl), bl - std::min(plen, bl));
     const int32_t nid = t->trie.find(joined.data(), joined.size());
     if (nid < 0) { delete t; return tok_fail(ZETT_ERR_INVALID, "merge result not in vocab: " + joined); }
-    t->merges[(static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b)] = {static_cast<int32_t>(r), nid};
+    t->merges.set((static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b), {static_cast<int32_t>(r), nid});
   }
   t->index_byte_pieces();
   *out = t;
