@@ -342,20 +342,23 @@ struct zett_tok {
     nxt.resize(n);
     for (int i = 0; i < n; ++i) { prev[i] = i - 1; nxt[i] = (i + 1 < n) ? i + 1 : -1; }
     struct Item { int32_t rank; int pos; int32_t new_id; };
-    auto cmp = [](const Item& a, const Item& b) {
+    auto cmp = [](const Item& a, const Item& b) {  // "a comes out after b": min-heap on (rank, pos, new id)
       if (a.rank != b.rank) return a.rank > b.rank;
       if (a.pos != b.pos) return a.pos > b.pos;
       return a.new_id > b.new_id;
     };
-    std::priority_queue<Item, std::vector<Item>, decltype(cmp)> heap(cmp);
+    thread_local std::vector<Item> heap;  // std::push_heap / pop_heap over per-thread storage: no allocation per token
+    heap.clear();
+    auto push = [&](Item it) { heap.push_back(it); std::push_heap(heap.begin(), heap.end(), cmp); };
     auto lookup = [&](int32_t a, int32_t b) -> const std::pair<int32_t, int32_t>* {
       return merges.find((static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b));
     };
     for (int i = 0; i + 1 < n; ++i)
-      if (auto* m = lookup(c[i], c[i + 1])) heap.push({m->first, i, m->second});
+      if (auto* m = lookup(c[i], c[i + 1])) push({m->first, i, m->second});
     while (!heap.empty()) {
-      const Item top = heap.top();
-      heap.pop();
+      std::pop_heap(heap.begin(), heap.end(), cmp);
+      const Item top = heap.back();
+      heap.pop_back();
       const int pos = top.pos;
       if (!alive[pos] || nxt[pos] == -1) continue;
       const int r = nxt[pos];
@@ -366,9 +369,9 @@ struct zett_tok {
       nxt[pos] = nxt[r];
       if (nxt[r] != -1) prev[nxt[r]] = pos;
       if (prev[pos] >= 0)
-        if (auto* m2 = lookup(c[prev[pos]], c[pos])) heap.push({m2->first, prev[pos], m2->second});
+        if (auto* m2 = lookup(c[prev[pos]], c[pos])) push({m2->first, prev[pos], m2->second});
       if (nxt[pos] != -1)
-        if (auto* m3 = lookup(c[pos], c[nxt[pos]])) heap.push({m3->first, pos, m3->second});
+        if (auto* m3 = lookup(c[pos], c[nxt[pos]])) push({m3->first, pos, m3->second});
     }
     for (int i = 0; i < n; ++i)
       if (alive[i]) out.push_back(c[i]);
