@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ZETT_B200_ABI_VERSION 1
+#define ZETT_B200_ABI_VERSION 2
 
 typedef enum zett_status {
   ZETT_OK = 0,
@@ -31,7 +31,9 @@ typedef enum zett_status {
   ZETT_ERR_STATE = -4,         /* call order (forward before finalize, missing weight ...)      (RuntimeError)        */
   ZETT_ERR_INDEX = -5,         /* a surface-form id outside [0, original_vocab_size + n_extra)  (IndexError)          */
   ZETT_ERR_KEY = -6,           /* a token char outside the 256-char byte alphabet               (KeyError)            */
-  ZETT_ERR_MISSING_UNK = -7    /* Unigram needed <unk> but the model has no unk id              (Exception)           */
+  ZETT_ERR_MISSING_UNK = -7,   /* Unigram needed <unk> but the model has no unk id              (Exception)           */
+  ZETT_ERR_RANGE = -8          /* a GEMM operand left fp16's range under split_terms = 2: rerun
+                                  after zett_hn_set_split_terms(h, 3)                            (ArithmeticError)     */
 } zett_status;
 
 const char* zett_last_error(void);
@@ -71,14 +73,15 @@ typedef struct zett_hn_config {
   float encoder_layer_norm_eps;            /* 1e-5 (roberta-base)                                                  */
   /* execution knobs, not model semantics */
   int32_t max_rows_per_pass;               /* rows handled by one pass of the kernels (0 -> 16384, transfer.py:44) */
-  int32_t gemm_impl;                       /* 0 = auto (5), 1 = tcgen05 1-CTA, 2 = tcgen05 CTA pairs (cta_group::2),
+  int32_t gemm_impl;                       /* 0 = auto (5), 2 = tcgen05 CTA pairs (cta_group::2) on 256 x 256 tiles,
                                               3 = SIMT fp32 debug kernel (checker, never the default),
-                                              4 = CTA pairs, two per cluster, W tile TMA-multicast between them,
                                               5 = CTA pairs on 256 x 512 tiles (N a multiple of 512, else as 2)    */
   int32_t split_terms;                     /* operand precision: 2 = fp16 MMA + two e5m2 correction MMAs at fp8 rate
-                                              (sizes must be multiples of 64), 3 = three bf16 MMA terms (A0W0 + A1W0
-                                              + A0W1), 0 = auto (2 when the sizes allow it, else 3), 1 = one bf16
-                                              pass (misses the 1e-3 parity budget; for comparison only)            */
+                                              (operands must stay inside fp16's range: zett_hn_check reports
+                                              ZETT_ERR_RANGE otherwise), 3 = three bf16 MMA terms (A0W0 + A1W0 + A0W1,
+                                              fp32's range), 0 = auto (2; the Python wrapper switches to 3 and reruns
+                                              on ZETT_ERR_RANGE), 1 = one bf16 pass (misses the 1e-3 parity budget;
+                                              for comparison only, announced on stderr)                            */
 } zett_hn_config;
 
 typedef struct zett_hn zett_hn;
@@ -96,8 +99,8 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out);
  * weight", "*.position_ids", "*.token_type_ids") are accepted and ignored. */
 int zett_hn_set_weight(zett_hn* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
 
-/* Checks that every weight the config needs is present, splits the Linear weights into the 16-bit planes the
- * tensor-core kernels consume, builds the TMA descriptors, frees the staging copies. */
+/* Checks that every weight the config needs is present and writes the Linear weights in the operand format the
+ * tensor-core kernels consume (the fp32 originals stay on the device for zett_hn_set_split_terms). */
 int zett_hn_finalize(zett_hn* h);
 
 /* Bytes of device workspace a forward of `n_rows` rows uses (allocated lazily by the library, reused across calls). */
@@ -114,9 +117,15 @@ int zett_hn_forward(zett_hn* h, const int32_t* surface_forms_dev, int64_t n_rows
                     int64_t v0_rows, int32_t lang_index, float* pred_in_dev, float* pred_out_dev,
                     float* pred_bias_dev, int64_t ld_pred, int64_t ld_bias, void* cuda_stream);
 
-/* Synchronises `cuda_stream` and reports what the kernels recorded: ZETT_ERR_INDEX if any surface-form id was
- * outside [0, V0 + max(n_extra, 1)) (the reference would raise an index error), ZETT_ERR_CUDA on a kernel fault. */
+/* Synchronises `cuda_stream` and reports what the kernels recorded since the previous check (the flags are sticky over
+ * any number of zett_hn_forward calls, and cleared here): ZETT_ERR_INDEX if any surface-form id was outside
+ * [0, V0 + max(n_extra, 1)) (the reference would raise an index error), ZETT_ERR_RANGE if a GEMM operand left fp16's
+ * range under split_terms = 2, ZETT_ERR_CUDA on a kernel fault. */
 int zett_hn_check(zett_hn* h, void* cuda_stream);
+
+/* Switch the operand format of a finalized handle (1, 2 or 3 as in zett_hn_config.split_terms): the Linear weights are
+ * rewritten from their fp32 originals and the workspace is re-sized on the next forward.  Synchronises the device. */
+int zett_hn_set_split_terms(zett_hn* h, int split_terms);
 
 /* Execution statistics of the last forward: kernels launched, packed (non-pad) positions, rows. */
 typedef struct zett_hn_stats {
@@ -132,6 +141,8 @@ typedef struct zett_hn_stats {
                                   LayerNorm and query/key/value GEMM run per pair); 0 when that is switched off    */
   int64_t split_terms;         /* the operand format in effect (zett_hn_config.split_terms after "auto")           */
   int64_t gemm_impl;           /* the GEMM implementation in effect (zett_hn_config.gemm_impl after "auto")         */
+  int64_t operand_overflows;   /* warps that produced a GEMM operand outside fp16's range since the previous
+                                  zett_hn_check (0 unless that check returned ZETT_ERR_RANGE)                       */
 } zett_hn_stats;
 int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out);
 
@@ -147,6 +158,16 @@ void zett_hn_destroy(zett_hn* h);
  * the CUDA-event time of `iters` back-to-back launches of the GEMM kernel alone (operands already split). */
 int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev, float* out_dev, int64_t m, int64_t n,
                   int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms, void* cuda_stream);
+
+/* The same with the whole epilogue: y = act(A W^T + bias) + residual[m, n];  y = col_scale[n] * y + col_shift[n]
+ * (every pointer after w_dev nullable).  out_operand_dev (nullable, fp32 [m, n]) receives the values DECODED from the
+ * operand-line output the kernel writes for the next GEMM (main plane + correction plane), so that a test can hold
+ * them against out_dev.  `report` (nullable, report_cap bytes) receives a JSON object with the per-role stall cycles
+ * of the last launch when the environment has ZETT_GEMM_PROF=1, else an empty string. */
+int zett_gemm_f32_ex(const float* a_dev, const float* w_dev, const float* bias_dev, const float* residual_dev,
+                     const float* col_scale_dev, const float* col_shift_dev, float* out_dev, float* out_operand_dev,
+                     int64_t m, int64_t n, int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms,
+                     char* report, int64_t report_cap, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Surface forms.

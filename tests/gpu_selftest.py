@@ -1,7 +1,7 @@
 """GPU self-test driver (run in a child process so that a kernel fault cannot poison the caller's CUDA context).
 
-    python tests/gpu_selftest.py gemm    --impl {1,2,3,4,5}
-    python tests/gpu_selftest.py forward --impl {1,2,3,4,5} [--configs tiny,tiny_lang,...] [--terms {1,2,3}]
+    python tests/gpu_selftest.py gemm    --impl {2,3,5}
+    python tests/gpu_selftest.py forward --impl {2,3,5} [--configs tiny,tiny_lang,...] [--terms {1,2,3}]
 
 Prints one JSON object per line: GEMM cases are checked against a float64 torch matmul of the SAME fp32 inputs,
 forward cases against the numpy oracle (oracle/hypernet_oracle.py).  ``tests/test_gpu_*.py`` assert on the lines.
@@ -30,6 +30,7 @@ GEMM_CASES = [
     (256, 256, 256, 0, 3),
     (200, 384, 192, 0, 3),      # ragged M, N = 3 x 128
     (77, 64, 128, 1, 3),        # tiny M, gelu tanh
+    (130, 72, 144, 0, 3),       # K and N not multiples of 32: padded lines, partial accumulator chunk
     (1000, 768, 768, 2, 3),     # XLM-R shapes, gelu erf
     (4096, 2304, 768, 0, 3),
     (3000, 4096, 4096, 0, 3),   # Mistral H x H
@@ -39,6 +40,7 @@ GEMM_CASES = [
     (2048, 4096, 4096, 0, 1),
     (128, 128, 64, 0, 2),       # fp16 + two e5m2 correction passes
     (200, 384, 192, 0, 2),
+    (130, 72, 144, 2, 2),
     (1000, 768, 768, 2, 2),
     (3000, 4096, 4096, 0, 2),
     (1024, 8192, 4096, 1, 2),
@@ -47,67 +49,130 @@ GEMM_CASES = [
     (16384, 4096, 4096, 0, 2),
 ]
 
+# whole-epilogue cases (zett_gemm_f32_ex): m, n, k, act, terms, residual, affine, operand output
+# M >= 16384, N % 512 == 0, K >= 4096 fill whole waves of 256 x 512 tiles, so gemm_impl 5 takes its wide branch
+GEMM_EX_CASES = [
+    (300, 256, 128, 1, 2, True, True, True),
+    (300, 256, 128, 2, 3, True, True, True),
+    (130, 72, 144, 1, 2, True, False, True),
+    (16384, 4096, 4096, 1, 2, True, False, True),
+    (16384, 4096, 4096, 2, 2, False, True, True),
+    (16384, 8192, 4096, 2, 2, False, False, True),
+    (16384, 4096, 8192, 0, 2, True, True, False),
+    (16384, 4096, 4096, 1, 3, True, True, True),
+    (18944, 1024, 4096, 2, 2, True, True, True),
+]
+
+
+def _gemm_ex(lib, a, w, b, res, cs, ct, out, out_op, act, impl, terms, iters=0, report=False):
+    m, k = a.shape
+    n = w.shape[0]
+    ms = ctypes.c_float(0)
+    buf = ctypes.create_string_buffer(1024) if report else None
+    ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.zett_gemm_f32_ex(ptr(a), ptr(w), ptr(b), ptr(res), ptr(cs), ptr(ct), ptr(out), ptr(out_op), m, n, k, act, impl,
+                                    terms, max(iters, 1), ctypes.byref(ms) if iters else None, buf, 1024 if report else 0, None))
+    rep = json.loads(buf.value.decode()) if (report and buf.value) else None
+    return ms.value, rep
+
+
+def _ref_gemm(a, w, b, act, res=None, cs=None, ct=None):
+    ref = a.double() @ w.double().T
+    if b is not None:
+        ref = ref + b.double()
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref, approximate="tanh")
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    if res is not None:
+        ref = ref + res.double()
+    if cs is not None:
+        ref = cs.double() * ref + ct.double()
+    return ref
+
 
 def run_gemm(impl: int):
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     ok = True
+    tol = {3: 5e-5, 2: 2e-4, 1: 2e-2}
     for (m, n, k, act, terms) in GEMM_CASES:
         a = torch.randn(m, k, device=dev)
         w = torch.randn(n, k, device=dev) / k ** 0.5
         b = torch.randn(n, device=dev) * 0.1
         out = torch.full((m, n), float("nan"), device=dev)
-        ms = ctypes.c_float(0)
         iters = 3
         try:
-            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, act, impl, terms,
-                                         iters, ctypes.byref(ms), None))
+            ms, _ = _gemm_ex(lib, a, w, b, None, None, None, out, None, act, impl, terms, iters=iters)
         except Exception as e:  # noqa: BLE001
             print(json.dumps(dict(kind="gemm", impl=impl, m=m, n=n, k=k, act=act, terms=terms, error=str(e))), flush=True)
             return False
-        ref = a.double() @ w.double().T + b.double()
-        if act == 1:
-            ref = torch.nn.functional.gelu(ref, approximate="tanh")
-        elif act == 2:
-            ref = torch.nn.functional.gelu(ref)
+        ref = _ref_gemm(a, w, b, act)
         err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
         fro = ((out.double() - ref).norm() / ref.norm()).item()
-        tol = {3: 5e-5, 2: 2e-4, 1: 2e-2}[terms]
-        good = bool(np.isfinite(err) and err < tol)
+        good = bool(np.isfinite(err) and err < tol[terms])
         ok &= good
-        tflops = 2.0 * m * n * k * iters / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+        tflops = 2.0 * m * n * k * iters / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         print(json.dumps(dict(kind="gemm", impl=impl, m=m, n=n, k=k, act=act, terms=terms, max_rel=err, fro_rel=fro,
-                              ok=good, ms_per_launch=ms.value / iters, tflops=tflops)), flush=True)
+                              ok=good, ms_per_launch=ms / iters, tflops=tflops)), flush=True)
+        del a, w, out, ref
+    for (m, n, k, act, terms, use_res, use_aff, use_op) in GEMM_EX_CASES:
+        a = torch.randn(m, k, device=dev)
+        w = torch.randn(n, k, device=dev) / k ** 0.5
+        b = torch.randn(n, device=dev) * 0.1
+        res = torch.randn(m, n, device=dev) if use_res else None
+        cs = (0.5 + torch.rand(n, device=dev)) if use_aff else None
+        ct = (torch.randn(n, device=dev) * 0.02) if use_aff else None
+        out = torch.full((m, n), float("nan"), device=dev)
+        out_op = torch.full((m, n), float("nan"), device=dev) if use_op else None
+        try:
+            _gemm_ex(lib, a, w, b, res, cs, ct, out, out_op, act, impl, terms)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps(dict(kind="gemm_ex", impl=impl, m=m, n=n, k=k, act=act, terms=terms, error=str(e))), flush=True)
+            return False
+        ref = _ref_gemm(a, w, b, act, res, cs, ct)
+        scale = ref.abs().max().item()
+        err = (out.double() - ref).abs().max().item() / scale
+        line = dict(kind="gemm_ex", impl=impl, m=m, n=n, k=k, act=act, terms=terms, residual=use_res, affine=use_aff,
+                    operand_out=use_op, max_rel=err)
+        good = bool(np.isfinite(err) and err < tol[terms])
+        if use_op:
+            # the operand lines written for the next GEMM decode to the fp32 output within the format's own resolution
+            # (fp16 + e5m2 residual: ~2^-13 of the value; bf16 hi + lo: ~2^-16)
+            d = (out_op.double() - out.double()).abs()
+            op_rel = (d / (out.double().abs() + 1e-3 * scale)).max().item()
+            line["operand_vs_f32"] = op_rel
+            good &= bool(np.isfinite(op_rel) and op_rel < (4e-4 if terms == 2 else 5e-5))
+        line["ok"] = good
+        ok &= good
+        print(json.dumps(line), flush=True)
+        del a, w, out, ref, res, out_op
     return ok
 
 
 def run_sweep():
-    """Timing probes of the GEMM engine (no parity claim): ms per launch over shapes x terms x rasterisation knobs."""
+    """Timing probes of the GEMM engine (no parity claim): ms per launch over shapes x formats x tile shapes, with the
+    per-role stall picture of one launch when ZETT_GEMM_PROF=1."""
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    shapes = [(16384, 4096, 4096), (16384, 4096, 8192), (53248, 12288, 4096), (65536, 8192, 4096), (65536, 4096, 8192)]
+    shapes = [(16384, 4096, 4096), (53248, 12288, 4096), (53248, 4096, 8192), (53248, 8192, 4096), (54000, 2304, 768),
+              (54000, 1536, 768), (54000, 768, 1536), (53248, 6144, 2048), (53248, 4096, 2048)]
     for (m, n, k) in shapes:
         a = torch.randn(m, k, device=dev)
         w = torch.randn(n, k, device=dev) / k ** 0.5
         b = torch.randn(n, device=dev) * 0.1
         out = torch.empty((m, n), device=dev)
-        for (chunk, group) in ((48, 4),):
-            os.environ["ZETT_RASTER_CHUNK_MB"] = str(chunk)
-            os.environ["ZETT_RASTER_GROUP_M"] = str(group)
-            for impl in (2, 4):
-                for terms in (3, 2, 1):
-                    ms = ctypes.c_float(0)
+        for impl in (2, 5):
+            for terms in (2, 3, 1):
+                for act in (0, 0x100, 2):
                     iters = 4
-                    _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, 0, impl,
-                                                 terms, iters, ctypes.byref(ms), None))
-                    t = ms.value / iters
-                    print(json.dumps(dict(kind="sweep", m=m, n=n, k=k, impl=impl, terms=terms, chunk_mb=chunk, group_m=group,
-                                          ms=round(t, 4), tflops=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1))), flush=True)
+                    ms, rep = _gemm_ex(lib, a, w, b, None, None, None, out, None, act, impl, terms, iters=iters, report=True)
+                    t = ms / iters
+                    print(json.dumps(dict(kind="sweep", m=m, n=n, k=k, impl=impl, terms=terms, act=act, ms=round(t, 4),
+                                          tflops=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), prof=rep)), flush=True)
         del a, w, out
-    os.environ.pop("ZETT_RASTER_CHUNK_MB", None)
-    os.environ.pop("ZETT_RASTER_GROUP_M", None)
     return True
 
 
@@ -151,55 +216,40 @@ def run_sustained(mnk_list, seconds=1.5):
         a = torch.randn(m, k, device=dev)
         w = torch.randn(n, k, device=dev) / k ** 0.5
         out = torch.empty((m, n), device=dev)
-        # (label, impl, terms, MMA mask, store the output?, environment)
-        W_LAST, A_FIRST, STREAM = {"ZETT_L2_HINT_W": "3"}, {"ZETT_L2_HINT_A": "1"}, {"ZETT_STREAM_OUT": "1"}
+        # (label, impl, terms, store the output?, environment)
+        W_LAST, STREAM = {"ZETT_L2_HINT_W": "3"}, {"ZETT_STREAM_OUT": "1"}
         variants = [
-            ("bf16x3", 2, 3, 7, True, {}),
-            ("bf16x3 W=evict_last", 2, 3, 7, True, W_LAST),
-            ("bf16x3 W=evict_last, streaming stores", 2, 3, 7, True, {**W_LAST, **STREAM}),
-            ("bf16x3 W=evict_last, A=evict_first, streaming stores", 2, 3, 7, True, {**W_LAST, **A_FIRST, **STREAM}),
-            ("bf16x3 streaming stores", 2, 3, 7, True, STREAM),
-            ("bf16x3 no store", 2, 3, 7, False, {}),
-            ("bf16x3 no MMA", 2, 3, 0, True, {}),
-            ("bf16x3 no MMA, no store (loads only)", 2, 3, 0, False, {}),
-            ("bf16x3 main term only", 2, 3, 1, True, {}),
-            ("f16+2xe5m2", 2, 2, 7, True, {}),
-            ("f16+2xe5m2 W=evict_last, streaming stores", 2, 2, 7, True, {**W_LAST, **STREAM}),
-            ("f16+2xe5m2 main term only", 2, 2, 1, True, {}),
-            ("f16+2xe5m2 fp8 terms only", 2, 2, 4, True, {}),
-            ("f16+2xe5m2 pairs of pairs", 4, 2, 7, True, {}),
-            ("f16+2xe5m2 256x512 tiles", 5, 2, 7, True, {}),
-            ("f16+2xe5m2 256x512 tiles no store", 5, 2, 7, False, {}),
-            ("f16+2xe5m2 no store", 2, 2, 7, False, {}),
-            ("f16+2xe5m2 256x512 tiles main term only", 5, 2, 1, True, {}),
-            ("bf16x3 256x512 tiles", 5, 3, 7, True, {}),
-            ("bf16 single pass", 2, 1, 7, True, {}),
-            ("bf16 single pass no store", 2, 1, 7, False, {}),
+            ("f16+2xe5m2 256x256", 2, 2, True, {}),
+            ("f16+2xe5m2 256x256 no store", 2, 2, False, {}),
+            ("f16+2xe5m2 256x512", 5, 2, True, {}),
+            ("f16+2xe5m2 256x512 no store", 5, 2, False, {}),
+            ("f16+2xe5m2 256x512 W=evict_last, streaming stores", 5, 2, True, {**W_LAST, **STREAM}),
+            ("bf16x3 256x256", 2, 3, True, {}),
+            ("bf16x3 256x512", 5, 3, True, {}),
+            ("bf16 single pass 256x256", 2, 1, True, {}),
+            ("bf16 single pass 256x256 no store", 2, 1, False, {}),
+            ("bf16 single pass 256x512", 5, 1, True, {}),
         ]
         only = os.environ.get("ZETT_SUSTAINED_ONLY")  # comma-separated substrings of the labels to keep
         if only:
             variants = [v for v in variants if any(tag in v[0] for tag in only.split(","))]
-        for (label, impl, terms, mask, store, env) in variants:
-            os.environ["ZETT_MMA_MASK"] = str(mask)
+        b = torch.zeros(n, device=dev)
+        for (label, impl, terms, store, env) in variants:
             for kk in ("ZETT_L2_HINT_W", "ZETT_L2_HINT_A", "ZETT_STREAM_OUT"):
                 os.environ.pop(kk, None)
             os.environ.update(env)
             act = 0 if store else 0x100
-            ms = ctypes.c_float(0)
-            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, act, impl, terms, 2,
-                                         ctypes.byref(ms), None))
-            iters = max(4, int(seconds * 1e3 / max(ms.value / 2, 1e-3)))
+            ms, _ = _gemm_ex(lib, a, w, b, None, None, None, out, None, act, impl, terms, iters=2)
+            iters = max(4, int(seconds * 1e3 / max(ms / 2, 1e-3)))
             ps = PowerSampler()
-            _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), None, out.data_ptr(), m, n, k, act, impl, terms, iters,
-                                         ctypes.byref(ms), None))
+            ms, _ = _gemm_ex(lib, a, w, b, None, None, None, out, None, act, impl, terms, iters=iters)
             st = ps.stop()
-            t = ms.value / iters
-            print(json.dumps(dict(kind="sustained", label=label, m=m, n=n, k=k, impl=impl, terms=terms, mma_mask=mask,
+            t = ms / iters
+            print(json.dumps(dict(kind="sustained", label=label, m=m, n=n, k=k, impl=impl, terms=terms,
                                   store=store, iters=iters, ms=round(t, 4),
                                   tflops_once=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), **st)), flush=True)
         for kk in ("ZETT_L2_HINT_W", "ZETT_L2_HINT_A", "ZETT_STREAM_OUT"):
             os.environ.pop(kk, None)
-        os.environ.pop("ZETT_MMA_MASK", None)
         ab, wb = a.bfloat16(), w.bfloat16()
         ob = torch.empty((m, n), device=dev, dtype=torch.bfloat16)
         for _ in range(3):
@@ -234,10 +284,8 @@ def run_one(m, n, k, impl, terms):
     w = torch.randn(n, k, device=dev) / k ** 0.5
     b = torch.randn(n, device=dev) * 0.1
     out = torch.empty((m, n), device=dev)
-    ms = ctypes.c_float(0)
-    _lib.check(lib.zett_gemm_f32(a.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, 0, impl, terms, 1,
-                                 ctypes.byref(ms), None))
-    print(json.dumps(dict(kind="one", m=m, n=n, k=k, impl=impl, terms=terms, ms=ms.value)), flush=True)
+    ms, rep = _gemm_ex(lib, a, w, b, None, None, None, out, None, 0, impl, terms, iters=1, report=True)
+    print(json.dumps(dict(kind="one", m=m, n=n, k=k, impl=impl, terms=terms, ms=ms, prof=rep)), flush=True)
     return True
 
 

@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, "ctypes signature missing for " + n
-    assert lib.zett_abi_version() == 1
+    assert lib.zett_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layout_matches_c():

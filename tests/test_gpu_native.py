@@ -27,9 +27,11 @@ def run_selftest(args, timeout=900):
     return r, lines
 
 
-@pytest.mark.parametrize("impl", [3, 1, 2, 4, 5])
+@pytest.mark.parametrize("impl", [3, 2, 5])
 def test_gemm_engine(impl):
-    """tcgen05 1-CTA / CTA pairs / pairs of pairs with W multicast / pairs on 256 x 512 tiles, and the SIMT checker against float64 matmul: 3-term split within 5e-5 of max |ref|."""
+    """tcgen05 CTA pairs on 256 x 256 tiles / on 256 x 512 tiles, and the SIMT checker, against a float64 matmul: every
+    operand format, ragged and padded sizes, and the whole epilogue (GELU, residual, column affine, operand-line output)
+    on shapes that take the wide-tile branch (M >= 16384, N % 512 == 0, K >= 4096)."""
     r, lines = run_selftest(["gemm", "--impl", str(impl)])
     assert lines, r.stdout + r.stderr
     for ln in lines:
@@ -38,7 +40,7 @@ def test_gemm_engine(impl):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("impl", [3, 1, 2, 4, 5])
+@pytest.mark.parametrize("impl", [3, 2, 5])
 def test_forward_tiny_configs(impl):
     """All tiny configurations (separate / tied heads, lang-id slot, single head, no rescale / bias, one layer,
     multi-pass) against the oracle: Frobenius and worst-row relative error <= 1e-3."""
@@ -234,7 +236,7 @@ def test_shape_variants(torch_cuda):
     torch = torch_cuda
     from oracle import hypernet_oracle as ho
     from zett_b200 import synthetic
-    # n_embd = 72: GEMM K = 144 is not a multiple of 64, so the automatic operand format falls back to the bf16 split
+    # n_embd = 72: GEMM K = 144 and N = 72 are not multiples of 32 (padded operand lines, partial accumulator chunks)
     for overrides in (dict(hn_n_layers=2, hn_surface_maxlen=12), dict(hn_num_attention_heads=4), dict(hn_num_attention_heads=1),
                       dict(n_embd=72)):
         cfg, weights, model = _model(torch, "tiny", **overrides)

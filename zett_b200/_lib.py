@@ -17,11 +17,12 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libzett_b200.so")
 SOURCES = ["hypernet.cu", "retok.cpp"]
-HEADERS = ["ptx.cuh", "gemm_tcgen05.cuh", "epilogue.cuh", "kernels.cuh"]
+HEADERS = ["ptx.cuh", "operand.cuh", "gemm_tcgen05.cuh", "epilogue.cuh", "kernels.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
-ZETT_OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_KEY, ERR_MISSING_UNK = 0, -1, -2, -3, -4, -5, -6, -7
+ZETT_OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_KEY, ERR_MISSING_UNK, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6, -7, -8
+ABI_VERSION = 2
 F32, F16, BF16 = 0, 1, 2
 
 
@@ -42,7 +43,7 @@ class ZettHnStats(ctypes.Structure):
     _fields_ = [("kernel_launches", c_int64), ("rows", c_int64), ("packed_positions", c_int64),
                 ("encoder_positions", c_int64), ("flops_executed", c_double), ("gemm_ms", c_double),
                 ("gemm_launches", c_int64), ("distinct_ids", c_int64), ("distinct_pairs", c_int64),
-                ("split_terms", c_int64), ("gemm_impl", c_int64)]
+                ("split_terms", c_int64), ("gemm_impl", c_int64), ("operand_overflows", c_int64)]
 
 
 def needs_build() -> bool:
@@ -87,11 +88,14 @@ SIGNATURES = {
     "zett_hn_forward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int64, c_void_p]),
     "zett_hn_check": (c_int, [c_void_p, c_void_p]),
+    "zett_hn_set_split_terms": (c_int, [c_void_p, c_int]),
     "zett_hn_get_stats": (c_int, [c_void_p, POINTER(ZettHnStats)]),
     "zett_hn_set_timing": (c_int, [c_void_p, c_int]),
     "zett_hn_destroy": (None, [c_void_p]),
     "zett_gemm_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                               c_int, POINTER(c_float), c_void_p]),
+    "zett_gemm_f32_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                 c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), c_char_p, c_int64, c_void_p]),
     "zett_tok_create_unigram": (c_int, [POINTER(c_char_p), POINTER(c_double), c_int64, c_int64, c_int, POINTER(c_void_p)]),
     "zett_tok_create_bpe": (c_int, [POINTER(c_char_p), c_int64, POINTER(c_int32), c_int64, c_int64, c_char_p, c_char_p,
                                     c_int, c_int, c_int, POINTER(c_void_p)]),
@@ -110,9 +114,10 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):  # a stale-but-present .so is rebuilt only by an explicit build()
+        stale = os.path.exists(LIB_PATH) and needs_build() and bool(shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"))
+        if not os.path.exists(LIB_PATH) or stale:  # sources newer than the .so: rebuild where a compiler exists
             try:
-                build()
+                build(force=stale)
             except Exception as e:  # noqa: BLE001
                 if not os.path.exists(LIB_PATH):
                     raise RuntimeError(
@@ -124,13 +129,18 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.zett_abi_version() != 1:
-            raise RuntimeError("libzett_b200.so ABI version mismatch")
+        if lib.zett_abi_version() != ABI_VERSION:
+            raise RuntimeError("libzett_b200.so ABI version mismatch: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         _lib = lib
         return lib
 
 
-_EXC = {ERR_INVALID: ValueError, ERR_UNSUPPORTED: NotImplementedError, ERR_CUDA: RuntimeError, ERR_STATE: RuntimeError,
+class OperandRangeError(ArithmeticError):
+    """A GEMM operand left fp16's range under split_terms = 2 (``ZETT_ERR_RANGE``): the forward has to be repeated with
+    the three-term bf16 split.  The wrappers in ``modeling_hypernet`` / ``transfer`` / ``parallel`` do that themselves."""
+
+
+_EXC = {ERR_RANGE: OperandRangeError, ERR_INVALID: ValueError, ERR_UNSUPPORTED: NotImplementedError, ERR_CUDA: RuntimeError, ERR_STATE: RuntimeError,
         ERR_INDEX: IndexError, ERR_KEY: KeyError, ERR_MISSING_UNK: Exception}
 
 

@@ -1,32 +1,31 @@
 // Persistent, warp-specialised tcgen05 GEMM for the hypernetwork's Linear layers:
 //     out[m, n] = epilogue( sum_k A[m, k] * W[n, k] )          (nn.Linear: y = x W^T + b, both operands K-major)
 //
-//  * operand formats (epilogue.cuh): 16-bit planes  plane 0 = round(x), plane 1 = round(x - plane 0)  issued as
-//    A0*B0 + A1*B0 + A0*B1 into the SAME TMEM accumulator (n_terms == 3; n_terms == 1 issues A0*B0 only), which restores
-//    ~fp32 operand precision (the 1e-3 parity budget rules out single-pass bf16); or fp16 + two e5m2
-//    correction planes (f8): one kind::f16 MMA + two kind::f8f6f4 MMAs per k-step.
-//  * warp 0 = TMA producer (3-D tensor maps {K, rows, plane}; 128-byte swizzle: 16-bit rows of BLOCK_K = 64, or the two
-//    fp8 planes of a k-block interleaved in one line), warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue
-//    (tcgen05.ld -> bias / GELU / residual / column affine -> fp32 and/or operand planes for the next GEMM).
-//  * n_halves == 1: accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
-//    main loop of tile i+1; smem stages form an mbarrier ring; every wait is bounded by a watchdog (ptx.cuh).
-//  * CG == 2 pairs two CTAs (cta_group::2, UMMA M = 256): each CTA loads its 128 rows of A and half of the B tile; the
-//    leader alone arrives on the full barrier (expecting both CTAs' bytes), issues the MMAs and multicasts the commits.
-//  * eight epilogue warps, two per TMEM lane quarter: the two groups of four take alternate 32-column chunks of one
-//    accumulator, or one N half each when n_halves == 2 (the epilogue is instruction-issue bound -- GELU, format
-//    conversion, 16-byte stores -- and with K = 768 it is as long as the main loop of a tile).
-//  * CP == 2 puts two such pairs in one cluster of four CTAs working on vertically adjacent 256-row tiles of the same
-//    N tile: every CTA fetches only HALF of its pair's share of the W tile and TMA-multicasts it to the CTA holding the
-//    same share in the other pair (.multicast::cluster), so a cluster reads 4 A blocks + 2 W blocks from the L2 slices
-//    instead of 4 + 4.  Measured: -19 % L2 slice reads, -16 % DRAM reads, but the bytes ARRIVING at
-//    each SM are unchanged and only 33 clusters of four fit the 148 SMs, so it ends within 2 % of plain pairs; kept as
-//    gemm_impl 4, not the default.  A smem stage of a CTA is then written by two CTAs, so every empty barrier counts one
-//    tcgen05.commit from EACH pair leader (multicast to all four CTAs); the full barriers stay per pair.
-//  * n_halves == 2 (gemm_impl 5) widens the tile of a CTA pair to 256 x 512: both accumulators of TMEM hold the two N halves
-//    of ONE tile, every k-block of A is fetched once for 512 columns (25 % fewer operand bytes per FLOP, the largest item of
-//    the kernel's energy budget after the MMAs), at the price of two 96 KB smem stages instead of
-//    three 64 KB ones and an epilogue that no longer overlaps the next tile's main loop.
+//  * Operands are rows of 128-byte lines (operand.cuh); ONE line per row is a pipeline stage: the A box is {128 B, 128
+//    rows}, the W box {128 B, this CTA's share of the tile's W rows}, both fetched with the 128-byte swizzle, one TMA
+//    each.  All product terms of a format (fp16 main term + two e5m2 correction terms; three bf16 terms; one bf16 term)
+//    are tcgen05.mma instructions on 32-byte K-slices of the same swizzled rows, accumulating into the SAME TMEM
+//    accumulator -- the list is a compile-time table (MmaList), so the issue loop is straight-line code.
+//  * A CTA pair (cta_group::2, UMMA M = 256) owns a tile: each CTA loads its 128 rows of A and its half of the W rows,
+//    only the leader arrives on the full barrier (expecting both CTAs' bytes) and issues the MMAs; commits are multicast.
+//  * Roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue.  Role dispatch is on a
+//    warp-uniform warp index and the producer / issuer loops run with all 32 lanes converged, electing one lane only
+//    around the asynchronous instructions: their operands (descriptors, barrier addresses, coordinates) then live in
+//    uniform registers.  (Round 1 branched on `lane == 0`; ptxas wrapped every tcgen05.mma in a five-R2UR waterfall
+//    loop, ~25 instructions per issue, and the single issuing thread could not keep the tensor pipe busy: 51 % active on
+//    the one-term probe.)
+//  * HALVES == 1: 256 x block_n tiles, two TMEM accumulators so the epilogue of tile i overlaps the main loop of tile
+//    i + 1.  HALVES == 2: 256 x 512 tiles, the two accumulators hold the two N halves of ONE tile: every line of A is
+//    fetched once for 512 columns (25 % fewer operand bytes per FLOP), the epilogue does not overlap the next main loop.
+//  * Epilogue: eight warps, two per TMEM lane quarter.  A warp reads a 32-lane x 32-column accumulator chunk
+//    (tcgen05.ld 32x32b.x32: one ROW per thread), transposes it through a private 4 KB shared-memory tile (16-byte
+//    chunks XOR-swizzled by row, conflict-free both ways) and continues with one QUAD per lane (epilogue.cuh): eight
+//    lanes cover 128 contiguous bytes of an output row, so residual loads, fp32 stores and operand-line stores are whole
+//    lines.  (Row-per-thread stores touch 32 lines per instruction; the LSU retires one line per cycle, which made the
+//    epilogue of a 256 x 512 tile 15 000 cycles long.)
 //  * M may live in device memory (packed-position counts are data dependent); tiles beyond it are skipped.
+//  * Every barrier wait is bounded by a watchdog (ptx.cuh).  With GemmShape::prof set, every role accumulates the cycles
+//    it spent waiting on each kind of barrier (the stall picture of one launch, read by the probes in tests/).
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -34,41 +33,38 @@
 
 namespace zett {
 
-constexpr int kBlockM = 128;
-constexpr int kMaxBlockK = 64;      // 64 x 2 B = one 128-byte swizzle row; block_k = 32 halves the rows (more, finer stages)
-constexpr int kUmmaK = 16;
+constexpr int kBlockM = 128;         // rows of A per CTA (UMMA M = 256 per pair)
 constexpr int kMaxStages = 8;
 constexpr int kEpilogueWarps = 8;    // two per TMEM lane quarter
 constexpr int kGemmThreads = 64 + 32 * kEpilogueWarps;   // TMA producer warp, MMA warp, epilogue warps
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kLineBytes = 128;
+constexpr uint32_t kABytes = kBlockM * kLineBytes;        // A part of a stage: 16 KB
+constexpr uint32_t kStagingBytes = kEpilogueWarps * 4096; // per-warp transpose tiles
+constexpr int kProfSlots = 8;        // per CTA: 0 total, 1 producer empty-wait, 2 MMA full-wait, 3 MMA accumulator-wait,
+                                     //          4 epilogue accumulator-wait (warp 2), 5 epilogue busy (warp 2), 6 tiles
 
 struct GemmShape {
   int m_host;          // rows of A / out when m_dev == nullptr
   const int* m_dev;    // optional device-resident row count
-  int n, k;
-  int block_n;         // UMMA N: 32, 64, 128 or 256
-  int n_halves;        // 1: tile N = block_n, accumulators double-buffered; 2: tile N = 2 * block_n (block_n == 256 only)
+  int n;
+  int k_lines;         // lines per operand row
+  int block_n;         // UMMA N: a multiple of 32 up to 256
   int group_m;         // rasterisation: m-tiles per group
   int chunk_n;         // rasterisation: n-tiles per L2-resident W chunk
-  int block_k;         // K elements per pipeline stage: 64 (128-byte rows of 16-bit operands) or 32
-  int n_terms;         // 1 or 3
-  int n_planes;        // planes held by the 16-bit tensor maps' boxes (1 or 2)
-  int f8;              // 1: operand format kFmtF16F8 -- one fp16 plane + two e5m2 correction planes (epilogue.cuh)
-  int mma_mask;        // diagnostic (ZETT_MMA_MASK, default 7): bit 0 main term, bit 1 16-bit correction terms, bit 2 fp8 terms
-  uint64_t hint_a, hint_b;   // L2 eviction policies of the A / W loads (ptx.cuh)
-  uint32_t idesc;      // tcgen05 instruction descriptor (kind::f16)
-  uint32_t idesc8;     // tcgen05 instruction descriptor (kind::f8f6f4), f8 only
   int num_stages;
-  uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;   // 16-bit planes: 128-byte rows
-  uint32_t a8_bytes, b8_bytes;                          // interleaved fp8 planes: 128-byte rows (q0[64] | q1[64])
+  uint32_t stage_bytes;
+  uint64_t hint_a, hint_b;   // L2 eviction policies of the A / W loads (ptx.cuh)
+  uint32_t idesc16;    // tcgen05 instruction descriptor, kind::f16
+  uint32_t idesc8;     // tcgen05 instruction descriptor, kind::f8f6f4 (e5m2 x e5m2)
+  unsigned long long* prof;  // nullable [gridDim.x, kProfSlots]
 };
 
 struct TileCoord { int m_blk, n_blk; };
 
-// Rasterisation for L2 residency (the main loop is bound by operand-fetch latency x limited smem buffering, so L2 hits
-// matter more than anything else): N is cut into chunks whose W panel fits comfortably in L2 and stays there while
-// all of M sweeps past it in small m-groups; inside a group m varies fastest, so the CTAs of a wave share W tiles
-// (one DRAM fetch, the rest L2 hits) and each A tile is fetched once per chunk.
+// Rasterisation for L2 residency: N is cut into chunks whose W panel stays in L2 while all of M sweeps past it in small
+// m-groups; inside a group m varies fastest, so the CTA pairs of a wave share W tiles and each A tile is fetched once per
+// chunk.
 __device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_tiles, int group_m, int chunk_n) {
   const int chunk_tiles = m_tiles * chunk_n;            // tiles of a full chunk
   const int c = tile / chunk_tiles;
@@ -86,194 +82,238 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_til
   return t;
 }
 
-// tmap_a / tmap_a8: box {block_k, 128 rows, all planes};  tmap_b / tmap_b8: box {block_k, block_n / (CG * CP) rows,
-// all planes (CP == 1) or ONE plane (CP == 2: a multicast share lands inside each plane of the [plane][row] smem layout)}
-template <int CG, int CP>
+// The tcgen05.mma instructions issued per line of K, as (kind is fp8?, byte offset of the A slice, of the W slice).
+template <int FMT> struct MmaList;
+template <> struct MmaList<kFmtF16F8> {
+  static constexpr int kCount = 4;
+  __device__ static constexpr bool f8(int i) { return i >= 2; }
+  __device__ static constexpr uint32_t a_off(int i) { return 32u * i; }   // p0[0:16] p0[16:32] | q0 | q1
+  __device__ static constexpr uint32_t b_off(int i) { return 32u * i; }
+};
+template <> struct MmaList<kFmtBf16x3> {
+  static constexpr int kCount = 6;
+  __device__ static constexpr bool f8(int) { return false; }
+  // hi.hi (two K slices), lo.hi, hi.lo
+  __device__ static constexpr uint32_t a_off(int i) { return i < 2 ? 32u * i : (i < 4 ? 64u + 32u * (i - 2) : 32u * (i - 4)); }
+  __device__ static constexpr uint32_t b_off(int i) { return i < 2 ? 32u * i : (i < 4 ? 32u * (i - 2) : 64u + 32u * (i - 4)); }
+};
+template <> struct MmaList<kFmtBf16x1> {
+  static constexpr int kCount = 4;
+  __device__ static constexpr bool f8(int) { return false; }
+  __device__ static constexpr uint32_t a_off(int i) { return 32u * i; }
+  __device__ static constexpr uint32_t b_off(int i) { return 32u * i; }
+};
+
+// hi word of the shared-memory matrix descriptor of a K-major, 128-byte-swizzled tile: stride between 8-row atoms 1024 B,
+// descriptor version 1 (bit 46), SWIZZLE_128B (bits 61-63 = 2); the lo word is (address >> 4) | leading-offset field 1
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (static_cast<uint64_t>(kDescHi) << 32) | static_cast<uint64_t>(((smem_addr & 0x3FFFFu) >> 4) | (1u << 16));
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+// One 32-row x 32-column accumulator chunk: `v` = this thread's row (tcgen05.ld layout); after the transpose lane l holds
+// the quad (row 4 i + l / 8, columns 4 (l % 8) ..) for i = 0..7.
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col0, int n,
+                                               const float (&v)[32], uint32_t& bad) {
+  const uint32_t wr = stg + static_cast<uint32_t>(lane) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((static_cast<uint32_t>(j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int jj = lane & 7, rsub = lane >> 3;
+  const int col = col0 + 4 * jj;
+  if (col < n) {
+    const QuadConsts q = load_quad_consts(ep, col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = 4 * i + rsub;
+      const float4 x = ld_shared_v4(stg + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(jj ^ (rr & 7)) << 4));
+      const long long row = row0 + rr;
+      if (row < M) epilogue_quad<ACT>(ep, row, col, x, q, bad);
+    }
+  }
+  __syncwarp();  // the tile is rewritten by the next chunk
+}
+
+__device__ __forceinline__ void epilogue_chunk_dyn(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col0, int n,
+                                                   const float (&v)[32], uint32_t& bad) {
+  if (ep.act == kActGeluTanh) epilogue_chunk<kActGeluTanh>(ep, stg, lane, row0, M, col0, n, v, bad);
+  else if (ep.act == kActGeluErf) epilogue_chunk<kActGeluErf>(ep, stg, lane, row0, M, col0, n, v, bad);
+  else epilogue_chunk<kActNone>(ep, stg, lane, row0, M, col0, n, v, bad);
+}
+
+// tmap_a: box {128 B, 128 rows} over A's lines;  tmap_b: box {128 B, HALVES * block_n / 2 rows} over W's lines
+template <int FMT, int HALVES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_a8, const __grid_constant__ CUtensorMap tmap_b8,
-                    const GemmShape s, const EpilogueParams ep) {
-  static_assert(CP == 1 || CG == 2, "pairs of pairs need cta_group::2");
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmShape s,
+                    const EpilogueParams ep) {
+  using L = MmaList<FMT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B swizzle atoms
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + s.num_stages * s.stage_bytes;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 1024-byte alignment for the 128B swizzle atoms
+  const uint32_t stg_base = smem_base + static_cast<uint32_t>(s.num_stages) * s.stage_bytes;
+  const uint32_t bar_base = stg_base + kStagingBytes;
   auto full_bar = [&](int i) { return bar_base + 8u * i; };
   auto empty_bar = [&](int i) { return bar_base + 8u * (kMaxStages + i); };
   auto tmem_full_bar = [&](int i) { return bar_base + 8u * (2 * kMaxStages + i); };
   auto tmem_empty_bar = [&](int i) { return bar_base + 8u * (2 * kMaxStages + 2 + i); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_index_uniform();
   const int lane = threadIdx.x & 31;
-  const uint32_t cluster_rank = (CG * CP > 1) ? cluster_ctarank() : 0u;
-  const uint32_t cta_rank = cluster_rank & (CG - 1);   // rank inside the CTA pair (cta_group::2 pairs ranks 2p, 2p + 1)
-  const uint32_t pair = cluster_rank / CG;             // pair inside the cluster
+  const uint32_t cta_rank = cluster_ctarank();   // rank inside the CTA pair
   const bool leader = cta_rank == 0;
 
-  const int M = s.m_dev ? *s.m_dev : s.m_host;
-  const int tile_m = kBlockM * CG * CP;                // rows of one cluster tile
+  // (shuffles from lane 0 tell the compiler these loaded values are warp-uniform: loop bounds and MMA operands derive from them)
+  const int M = __shfl_sync(0xFFFFFFFFu, s.m_dev ? *s.m_dev : s.m_host, 0);
+  constexpr int tile_m = 2 * kBlockM;
   const int m_tiles = (M + tile_m - 1) / tile_m;
-  const int tile_n = s.block_n * s.n_halves;
+  const int tile_n = s.block_n * HALVES;
   const int n_tiles = (s.n + tile_n - 1) / tile_n;
   const int total_tiles = m_tiles * n_tiles;
-  const int num_kb = (s.k + s.block_k - 1) / s.block_k;
-  const int first_tile = blockIdx.x / (CG * CP);
-  const int tile_step = gridDim.x / (CG * CP);
-  const int load_n = s.block_n / CG;  // rows of the W tile this CTA's smem holds, per N half
-  const int cta_row0 = static_cast<int>(pair) * kBlockM * CG + static_cast<int>(cta_rank) * kBlockM;  // inside the cluster tile
+  const int num_kb = s.k_lines;
+  const int first_tile = blockIdx.x >> 1;
+  const int tile_step = gridDim.x >> 1;
+  const int load_n = s.block_n >> 1;  // rows of the W tile this CTA's smem holds, per N half
+  const bool prof = s.prof != nullptr;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    if (s.f8) {
-      prefetch_tmap(&tmap_a8);
-      prefetch_tmap(&tmap_b8);
-    }
     for (int i = 0; i < s.num_stages; ++i) {
       mbar_init(full_bar(i), 1);    // the leader's arrive.expect_tx covers the bytes landing in both CTAs of the pair
-      mbar_init(empty_bar(i), CP);  // one tcgen05.commit per pair that reads or multicasts into this stage
+      mbar_init(empty_bar(i), 1);   // one tcgen05.commit (multicast to both CTAs)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full_bar(i), 1);
-      // every epilogue thread that reads this accumulator, in every CTA of the pair: both warp groups (n_halves == 1)
-      // or the one group that owns this N half (n_halves == 2)
-      mbar_init(tmem_empty_bar(i), (s.n_halves == 2 ? 128 : 256) * CG);
+      // one arrival per epilogue warp that reads this accumulator, in both CTAs of the pair: all eight warps
+      // (HALVES == 1) or the four that own this N half (HALVES == 2)
+      mbar_init(tmem_empty_bar(i), (HALVES == 2 ? 4 : 8) * 2);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<CG>(tmem_slot, kTmemCols);
+  if (warp == 1) tmem_alloc<2>(tmem_slot, kTmemCols);
   tc_fence_before();
-  if constexpr (CG * CP > 1) cluster_sync_all(); else __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
 
   if (warp == 0) {
     // ===================================== TMA producer ==========================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
-        const int row_a = tc.m_blk * tile_m + cta_row0;
-        const int row_b = tc.n_blk * tile_n + static_cast<int>(cta_rank) * load_n * s.n_halves;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-          const uint32_t a_dst = smem_base + stage * s.stage_bytes;
-          const uint32_t b_dst = a_dst + s.n_planes * s.a_plane_bytes;
-          const uint32_t a8_dst = b_dst + s.n_planes * s.b_plane_bytes;
-          const uint32_t b8_dst = a8_dst + s.a8_bytes;
-          if constexpr (CG == 1) {
-            mbar_expect_tx(full_bar(stage), s.stage_bytes);
-            tma_load_3d(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0, s.hint_a);
-            tma_load_3d(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0, s.hint_b);
-            if (s.f8) {
-              tma_load_3d(&tmap_a8, full_bar(stage), a8_dst, kb * 128, row_a, 0, s.hint_a);
-              tma_load_3d(&tmap_b8, full_bar(stage), b8_dst, kb * 128, row_b, 0, s.hint_b);
-            }
-          } else {
-            // only the leader arrives (expecting the bytes landing in both CTAs of its pair); the other copies credit
-            // that barrier directly, so no other loop carries a cluster-scope operation.  Bytes may land before the
-            // leader's expect_tx: the phase cannot complete until that arrive, and the transaction count is signed.
-            if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
-            tma_load_3d_2sm(&tmap_a, full_bar(stage), a_dst, kb * s.block_k, row_a, 0, s.hint_a);
-            if (s.f8) tma_load_3d_2sm(&tmap_a8, full_bar(stage), a8_dst, kb * 128, row_a, 0, s.hint_a);
-            if constexpr (CP == 1) {
-              tma_load_3d_2sm(&tmap_b, full_bar(stage), b_dst, kb * s.block_k, row_b, 0, s.hint_b);
-              if (s.f8) tma_load_3d_2sm(&tmap_b8, full_bar(stage), b8_dst, kb * 128, row_b, 0, s.hint_b);
-            } else {
-              // this CTA fetches rows [pair * load_n / 2, +load_n / 2) of its share, plane by plane, for itself and for the
-              // CTA of equal pair rank in the other pair; the other half arrives from there.  Each copy credits the full
-              // barrier of the destination's own pair leader.
-              const int share = load_n / CP;
-              const int row_s = row_b + static_cast<int>(pair) * share;
-              const uint16_t mask = static_cast<uint16_t>(0x5u << cta_rank);
-              const uint32_t off16 = pair * static_cast<uint32_t>(share) * static_cast<uint32_t>(s.block_k) * 2u;
-              for (int pl = 0; pl < s.n_planes; ++pl)
-                tma_load_3d_2sm_mc(&tmap_b, full_bar(stage), b_dst + pl * s.b_plane_bytes + off16, kb * s.block_k, row_s, pl, mask, s.hint_b);
-              if (s.f8)
-                tma_load_3d_2sm_mc(&tmap_b8, full_bar(stage), b8_dst + pair * static_cast<uint32_t>(share) * 128u, kb * 128, row_s, 0, mask, s.hint_b);
-            }
-          }
-          if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
+    int stage = 0;
+    uint32_t phase = 0;
+    long long waited = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
+      const int row_a = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
+      const int row_b = tc.n_blk * tile_n + static_cast<int>(cta_rank) * load_n * HALVES;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const long long t0 = prof ? clock64() : 0;
+        mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+        if (prof) waited += clock64() - t0;
+        if (elect_one()) {
+          // only the leader arrives (expecting the bytes landing in both CTAs of the pair); the copies of both CTAs credit
+          // that barrier.  Bytes may land before the expect_tx: the phase cannot complete until that arrive.
+          if (leader) mbar_expect_tx(full_bar(stage), s.stage_bytes * 2u);
+          const uint32_t a_dst = smem_base + static_cast<uint32_t>(stage) * s.stage_bytes;
+          tma_load_2d_2sm(&tmap_a, full_bar(stage), a_dst, kb * static_cast<int>(kLineBytes), row_a, s.hint_a);
+          tma_load_2d_2sm(&tmap_b, full_bar(stage), a_dst + kABytes, kb * static_cast<int>(kLineBytes), row_b, s.hint_b);
         }
+        __syncwarp();
+        if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
       }
     }
+    if (prof && lane == 0) s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 1] = static_cast<unsigned long long>(waited);
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
-    if (lane == 0 && leader) {
-      const uint16_t kAllMask = static_cast<uint16_t>((1u << (CG * CP)) - 1u);
-      const uint16_t kPairMask = static_cast<uint16_t>(((1u << CG) - 1u) << (pair * CG));
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      long long waited_full = 0, waited_acc = 0;
+      const uint32_t half_bytes = static_cast<uint32_t>(load_n) * kLineBytes;   // W rows of one N half in this CTA's stage
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase, 3);
-          tc_fence_after();
-          const uint32_t a0 = smem_base + stage * s.stage_bytes;
-          const uint32_t b0 = a0 + s.n_planes * s.a_plane_bytes;
-          const uint32_t row16 = static_cast<uint32_t>(s.block_k) * 2u;  // bytes per row of a 16-bit plane
-          const uint64_t da0 = umma_desc_kmajor(a0, row16), da1 = umma_desc_kmajor(a0 + s.a_plane_bytes, row16);
-          const uint32_t a8 = b0 + s.n_planes * s.b_plane_bytes;
-          const uint64_t dqa = umma_desc_kmajor(a8, 128u);
-          const int ksteps = s.block_k / kUmmaK;
-          for (int hf = 0; hf < s.n_halves; ++hf) {
-            // accumulator: the N half of the tile (n_halves == 2) or the buffer this tile alternates to (n_halves == 1)
-            const int acc = s.n_halves == 2 ? hf : (iter & 1);
-            if (kb == 0) {
-              const uint32_t acc_phase = s.n_halves == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
-              mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u, 2);
-              tc_fence_after();
+          if (kb == 0) {
+            const long long t0 = prof ? clock64() : 0;
+            if (HALVES == 2) {
+              mbar_wait(tmem_empty_bar(0), (iter & 1u) ^ 1u, 2);
+              mbar_wait(tmem_empty_bar(1), (iter & 1u) ^ 1u, 2);
+            } else {
+              mbar_wait(tmem_empty_bar(iter & 1), ((iter >> 1) & 1u) ^ 1u, 2);
             }
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * s.block_n);
-            const uint32_t bh = b0 + static_cast<uint32_t>(hf * load_n) * row16;  // this half's rows of the W planes
-            const uint64_t db0 = umma_desc_kmajor(bh, row16), db1 = umma_desc_kmajor(bh + s.b_plane_bytes, row16);
-#pragma unroll 4
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint64_t koff = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);  // 32 B per K step inside the atom
-              if (s.mma_mask & 1) umma_f16<CG>(tmem_d, da0 + koff, db0 + koff, s.idesc, (kb | kk) != 0);
-              if (s.n_terms == 3 && !s.f8 && (s.mma_mask & 2)) {
-                umma_f16<CG>(tmem_d, da1 + koff, db0 + koff, s.idesc, 1u);
-                umma_f16<CG>(tmem_d, da0 + koff, db1 + koff, s.idesc, 1u);
-              }
-            }
-            if (s.f8 && (s.mma_mask & 4)) {  // first-order corrections at fp8 rate: Aq0 . Wq0 + Aq1 . Wq1, K = 32 per instruction
-              const uint64_t dqb = umma_desc_kmajor(a8 + s.a8_bytes + static_cast<uint32_t>(hf * load_n) * 128u, 128u);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)  // bytes [0, 64) of a row are q0 of the k-block, [64, 128) are q1
-                umma_f8<CG>(tmem_d, dqa + 2u * kk, dqb + 2u * kk, s.idesc8, (s.mma_mask & 1) | kb | kk);
-            }
-            if (kb == num_kb - 1) umma_commit<CG>(tmem_full_bar(acc), kPairMask);  // accumulator complete (this pair)
+            if (prof) waited_acc += clock64() - t0;
           }
-          umma_commit<CG>(empty_bar(stage), kAllMask);                            // frees the stage in every CTA of the cluster
+          const long long t1 = prof ? clock64() : 0;
+          mbar_wait(full_bar(stage), phase, 3);
+          if (prof) waited_full += clock64() - t1;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = smem_base + static_cast<uint32_t>(stage) * s.stage_bytes;
+            const uint64_t da = make_desc(a0);
+#pragma unroll
+            for (int hf = 0; hf < HALVES; ++hf) {
+              // accumulator: the N half of the tile (HALVES == 2) or the buffer this tile alternates to (HALVES == 1)
+              const int acc = HALVES == 2 ? hf : (iter & 1);
+              const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * s.block_n);
+              const uint64_t db = make_desc(a0 + kABytes + static_cast<uint32_t>(hf) * half_bytes);
+#pragma unroll
+              for (int i = 0; i < L::kCount; ++i) {
+                const uint32_t accumulate = (i > 0 || kb > 0) ? 1u : 0u;
+                if (L::f8(i)) umma_f8<2>(tmem_d, da + (L::a_off(i) >> 4), db + (L::b_off(i) >> 4), s.idesc8, accumulate);
+                else umma_f16<2>(tmem_d, da + (L::a_off(i) >> 4), db + (L::b_off(i) >> 4), s.idesc16, accumulate);
+              }
+              if (kb == num_kb - 1) umma_commit<2>(tmem_full_bar(acc), 3);   // accumulator complete -> both CTAs' epilogues
+            }
+            umma_commit<2>(empty_bar(stage), 3);                              // frees the stage in both CTAs
+          }
+          __syncwarp();
           if (++stage == s.num_stages) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (prof && lane == 0) {
+        s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 2] = static_cast<unsigned long long>(waited_full);
+        s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 3] = static_cast<unsigned long long>(waited_acc);
       }
     }
   } else {
     // ===================================== epilogue warps ========================================
     const int quarter = warp & 3;        // TMEM lanes [32 * quarter, 32 * quarter + 32) are the ones this warp may read
     const int group = (warp - 2) >> 2;   // 0 or 1
+    const uint32_t stg = stg_base + static_cast<uint32_t>(warp - 2) * 4096u;
+    uint32_t bad = 0;
+    long long waited = 0, busy = 0;
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
-      const int row = tc.m_blk * tile_m + cta_row0 + quarter * 32 + lane;
-      const bool row_ok = row < M;
-      // n_halves == 2: group g drains N half g.  n_halves == 1: both groups drain the tile's accumulator, group g taking
+      const long long row0 = static_cast<long long>(tc.m_blk) * tile_m + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
+      // HALVES == 2: group g drains N half g.  HALVES == 1: both groups drain the tile's accumulator, group g taking
       // the 32-column chunks g, g + 2, ...
-      const int hf = s.n_halves == 2 ? group : 0;
-      const int acc = s.n_halves == 2 ? hf : (iter & 1);
-      const uint32_t acc_phase = s.n_halves == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
-      const int c_first = s.n_halves == 2 ? 0 : 32 * group;
-      const int c_step = s.n_halves == 2 ? 32 : 64;
+      const int hf = HALVES == 2 ? group : 0;
+      const int acc = HALVES == 2 ? hf : (iter & 1);
+      const uint32_t acc_phase = HALVES == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
+      const int c_first = HALVES == 2 ? 0 : 32 * group;
+      const int c_step = HALVES == 2 ? 32 : 64;
+      const long long t0 = prof ? clock64() : 0;
       mbar_wait(tmem_full_bar(acc), acc_phase, 4);
+      const long long t1 = prof ? clock64() : 0;
       tc_fence_after();
       // accumulator column c holds W row (c < load_n ? CTA 0's : CTA 1's) share of this half:
-      //   output column = tile origin + (c / load_n) * load_n * n_halves + hf * load_n + c % load_n   (= origin + c when n_halves == 1)
+      //   output column = tile origin + (c / load_n) * load_n * HALVES + hf * load_n + c % load_n   (= origin + c when HALVES == 1)
       const int col_tile = tc.n_blk * tile_n + hf * load_n;
-      auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (s.n_halves - 1)); };
+      auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (HALVES - 1)); };
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
       // two register chunks: the tcgen05.ld of the next chunk is in flight while the current one is processed
       float va[32], vb[32];
@@ -282,23 +322,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int c2 = c + c_step, c3 = c2 + c_step;
         tmem_ld_wait();
         if (c2 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c2), vb);
-        if (row_ok && gcol(c) < s.n) epilogue_store32(ep, row, gcol(c), min(32, s.n - gcol(c)), va);
+        if (gcol(c) < s.n) epilogue_chunk_dyn(ep, stg, lane, row0, M, gcol(c), s.n, va, bad);
         if (c2 < s.block_n) {
           tmem_ld_wait();
           if (c3 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c3), va);
-          if (row_ok && gcol(c2) < s.n) epilogue_store32(ep, row, gcol(c2), min(32, s.n - gcol(c2)), vb);
+          if (gcol(c2) < s.n) epilogue_chunk_dyn(ep, stg, lane, row0, M, gcol(c2), s.n, vb, bad);
         }
       }
       tc_fence_before();
-      if constexpr (CG == 1) mbar_arrive(tmem_empty_bar(acc));
-      else mbar_arrive_cluster(tmem_empty_bar(acc), pair * CG);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(acc), 0);   // the leader's barrier
+      if (prof) { waited += t1 - t0; busy += clock64() - t1; }
+    }
+    report_saturation(ep.out_op.sat, bad);
+    if (prof && warp == 2 && lane == 0) {
+      s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 4] = static_cast<unsigned long long>(waited);
+      s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 5] = static_cast<unsigned long long>(busy);
+      s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 6] = static_cast<unsigned long long>(iter);
     }
   }
 
   __syncwarp();
   tc_fence_before();
-  if constexpr (CG * CP > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) tmem_dealloc<CG>(tmem_base, kTmemCols);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc<2>(tmem_base, kTmemCols);
+  if (prof && threadIdx.x == 0) s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots] = static_cast<unsigned long long>(clock64() - t_start);
 }
 
 }  // namespace zett

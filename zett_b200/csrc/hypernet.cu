@@ -65,47 +65,22 @@ int get_encode_fn(EncodeTiledFn* out) {
   return ZETT_OK;
 }
 
-// 3-D map {K, rows, planes} over 16-bit planes, box {block_k, box_rows, box_planes}, 128-byte swizzle, zero fill out of bounds
-CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
-  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
-
-int make_plane_tmap(CUtensorMap* map, const uint16_t* base, long long rows, long long k, long long plane_stride_elems,
-                    int box_rows, int n_planes, int box_planes, int split_fmt, int block_k) {
+// 2-D map over operand lines (operand.cuh): {ld_bytes, rows} bytes, box {128 bytes, box_rows}, 128-byte swizzle, zero fill
+// out of bounds
+int make_line_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long ld_bytes, int box_rows) {
   EncodeTiledFn enc;
   ZETT_TRY(get_encode_fn(&enc));
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(n_planes)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(k) * 2u, static_cast<cuuint64_t>(plane_stride_elems) * 2u};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_planes)};
-  cuuint32_t estr[3] = {1, 1, 1};
-  if (n_planes == 1) strides[1] = strides[0] * static_cast<cuuint64_t>(rows);
-  const CUtensorMapDataType dt = split_fmt == kFmtBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUresult r = enc(map, dt, 3, const_cast<uint16_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_for_row_bytes(block_k * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%lld k=%lld plane_stride=%lld box_rows=%d planes=%d",
-             static_cast<int>(r), rows, k, plane_stride_elems, box_rows, n_planes);
-    return fail(ZETT_ERR_CUDA, buf);
-  }
-  return ZETT_OK;
-}
-
-// map over the interleaved e5m2 correction planes (epilogue.cuh): rows of 2 K bytes, box {128 bytes, box_rows}, 128-byte swizzle
-int make_plane8_tmap(CUtensorMap* map, const uint8_t* base, long long rows, long long k, int box_rows) {
-  EncodeTiledFn enc;
-  ZETT_TRY(get_encode_fn(&enc));
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(2 * k), static_cast<cuuint64_t>(rows), 1};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(2 * k), static_cast<cuuint64_t>(2 * k) * static_cast<cuuint64_t>(rows)};
-  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(ld_bytes), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_bytes)};
+  cuuint32_t box[2] = {128, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (fp8 planes) failed (%d): rows=%lld k=%lld box_rows=%d", static_cast<int>(r), rows, k,
-             box_rows);
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rows=%lld ld_bytes=%lld box_rows=%d", static_cast<int>(r), rows,
+             ld_bytes, box_rows);
     return fail(ZETT_ERR_CUDA, buf);
   }
   return ZETT_OK;
@@ -142,6 +117,11 @@ std::string watchdog_text() {
   return buf;
 }
 
+template <int FMT, int HALVES>
+cudaError_t set_gemm_smem() {
+  return cudaFuncSetAttribute(gemm_tcgen05_kernel<FMT, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
+
 int set_kernel_attrs(DeviceInfo* d) {
   if (d->attrs_set) return ZETT_OK;
   if (!g_watchdog_host) {
@@ -151,9 +131,12 @@ int set_kernel_attrs(DeviceInfo* d) {
   unsigned long long* dptr = nullptr;
   ZETT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_watchdog_host, 0));
   ZETT_CUDA(cudaMemcpyToSymbol(g_zett_watchdog, &dptr, sizeof dptr));
-  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  ZETT_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  ZETT_CUDA((set_gemm_smem<kFmtF16F8, 1>()));
+  ZETT_CUDA((set_gemm_smem<kFmtF16F8, 2>()));
+  ZETT_CUDA((set_gemm_smem<kFmtBf16x3, 1>()));
+  ZETT_CUDA((set_gemm_smem<kFmtBf16x3, 2>()));
+  ZETT_CUDA((set_gemm_smem<kFmtBf16x1, 1>()));
+  ZETT_CUDA((set_gemm_smem<kFmtBf16x1, 2>()));
   ZETT_CUDA(cudaFuncSetAttribute(gather_rescale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
   d->attrs_set = true;
   return ZETT_OK;
@@ -161,13 +144,11 @@ int set_kernel_attrs(DeviceInfo* d) {
 
 // ---- GEMM launcher ------------------------------------------------------------------------------------------------
 struct GemmArgs {
-  const uint16_t* a = nullptr;     // plane 0 of A, [a_rows, k]
+  const uint8_t* a = nullptr;      // operand lines of A, [a_rows, a_ld bytes]
   long long a_rows = 0;            // rows the A buffer holds (TMA bound)
-  long long a_plane_stride = 0;    // elements between plane 0 and plane 1
-  const uint16_t* w = nullptr;     // plane 0 of W, [n, k]
-  long long w_plane_stride = 0;
-  const uint8_t* a_q = nullptr;    // kFmtF16F8: interleaved fp8 planes of A / W, rows of 2 K bytes
-  const uint8_t* w_q = nullptr;
+  long long a_ld = 0;
+  const uint8_t* w = nullptr;      // operand lines of W, [n, w_ld bytes]
+  long long w_ld = 0;
   int n = 0, k = 0;
   int m_host = 0;
   const int* m_dev = nullptr;
@@ -176,16 +157,26 @@ struct GemmArgs {
 
 struct GemmEngine {
   DeviceInfo dev;
-  int impl = 5;        // 1: tcgen05 1-CTA, 2: tcgen05 CTA pairs, 3: SIMT, 4: CTA pairs, two per cluster, W multicast,
-                       // 5: CTA pairs on 256 x 512 tiles (both TMEM accumulators hold one tile)
-  int max_clusters4 = -1;  // co-resident clusters of four CTAs (queried once; GPC sizes decide it)
-  int n_terms = 3;     // 3: 16-bit three-term split, 1: single 16-bit pass, 2: fp16 + two e5m2 correction passes
-  int split_fmt = kFmtBf16;
-  std::map<std::tuple<const void*, long long, long long, long long, int, int>, CUtensorMap> tmaps;
+  int impl = 5;        // 2: CTA pairs on 256 x block_n tiles, 3: SIMT checker, 5: pairs on 256 x 512 tiles where they pay
+  int n_terms = 2;     // 2: fp16 + two e5m2 correction terms, 3: three bf16 terms, 1: one bf16 pass (probes only)
+  int fmt = kFmtF16F8;
+  std::map<std::tuple<const void*, long long, long long, int>, CUtensorMap> tmaps;
+  long long launches = 0;
+  long long raster_chunk_bytes = 48ll << 20;
+  int raster_group_m = 4;
+  int wide_min_k = 4096;   // 256 x 512 tiles are used from this K on (their epilogue does not overlap the next main loop)
+  uint64_t hint_a = kL2EvictNormal, hint_b = kL2EvictNormal;  // L2 eviction policies of the operand loads
+  bool stream_out = false; // fp32 outputs stored with the streaming hint
+  unsigned long long* prof_dev = nullptr;   // ZETT_GEMM_PROF=1: per-CTA stall counters of the last launch (probes)
+  // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
+  bool timing = false;
+  std::vector<cudaEvent_t> events;
+  size_t events_used = 0;
+
   void read_env() {
     if (const char* e = getenv("ZETT_RASTER_CHUNK_MB")) raster_chunk_bytes = std::max(1ll, atoll(e)) << 20;
     if (const char* e = getenv("ZETT_RASTER_GROUP_M")) raster_group_m = std::max(1, atoi(e));
-    if (const char* e = getenv("ZETT_BLOCK_K")) block_k = atoi(e) == 32 ? 32 : 64;
+    if (const char* e = getenv("ZETT_WIDE_MIN_K")) wide_min_k = std::max(32, atoi(e));
     auto hint = [](const char* e, uint64_t dflt) -> uint64_t {
       if (!e) return dflt;
       const int v = atoi(e);
@@ -194,23 +185,18 @@ struct GemmEngine {
     hint_a = hint(getenv("ZETT_L2_HINT_A"), hint_a);   // 1 evict_first, 2 normal, 3 evict_last
     hint_b = hint(getenv("ZETT_L2_HINT_W"), hint_b);
     if (const char* e = getenv("ZETT_STREAM_OUT")) stream_out = atoi(e) != 0;
-    if (const char* e = getenv("ZETT_MMA_MASK")) mma_mask = atoi(e) & 7;  // energy / throughput probes only: results are wrong
+    if (getenv("ZETT_GEMM_PROF") && !prof_dev) {
+      if (cudaMalloc(&prof_dev, sizeof(unsigned long long) * 256 * kProfSlots) != cudaSuccess) prof_dev = nullptr;
+    }
   }
   void set_precision(int terms) {
-    n_terms = (terms == 1 || terms == 2) ? terms : 3;
-    split_fmt = n_terms == 2 ? kFmtF16F8 : kFmtBf16;
+    n_terms = (terms == 1 || terms == 3) ? terms : 2;
+    fmt = n_terms == 2 ? kFmtF16F8 : (n_terms == 3 ? kFmtBf16x3 : kFmtBf16x1);
   }
-  long long launches = 0;
-  // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
-  long long raster_chunk_bytes = 48ll << 20;
-  int raster_group_m = 4;
-  int block_k = 64;        // K per pipeline stage (64 or 32)
-  int mma_mask = 7;        // diagnostic: which product terms are issued (gemm_tcgen05.cuh)
-  uint64_t hint_a = kL2EvictNormal, hint_b = kL2EvictNormal;  // L2 eviction policies of the operand loads
-  bool stream_out = false; // fp32 outputs stored with the streaming hint
-  bool timing = false;
-  std::vector<cudaEvent_t> events;
-  size_t events_used = 0;
+  ~GemmEngine() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    if (prof_dev) cudaFree(prof_dev);
+  }
 
   int time_mark(cudaStream_t stream) {
     if (!timing) return ZETT_OK;
@@ -234,25 +220,12 @@ struct GemmEngine {
     return total;
   }
 
-  int tmap(const uint16_t* base, long long rows, long long k, long long plane_stride, int box_rows, int n_planes,
-           int box_planes, const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, plane_stride, box_rows + 1000 * block_k,
-                               n_planes + 16 * box_planes);
+  int tmap(const uint8_t* base, long long rows, long long ld_bytes, int box_rows, const CUtensorMap** out) {
+    auto key = std::make_tuple(static_cast<const void*>(base), rows, ld_bytes, box_rows);
     auto it = tmaps.find(key);
     if (it == tmaps.end()) {
       CUtensorMap m;
-      ZETT_TRY(make_plane_tmap(&m, base, rows, k, plane_stride, box_rows, n_planes, box_planes, split_fmt, block_k));
-      it = tmaps.emplace(key, m).first;
-    }
-    *out = &it->second;
-    return ZETT_OK;
-  }
-  int tmap8(const uint8_t* base, long long rows, long long k, int box_rows, const CUtensorMap** out) {
-    auto key = std::make_tuple(static_cast<const void*>(base), rows, k, 0ll, box_rows, 8);
-    auto it = tmaps.find(key);
-    if (it == tmaps.end()) {
-      CUtensorMap m;
-      ZETT_TRY(make_plane8_tmap(&m, base, rows, k, box_rows));
+      ZETT_TRY(make_line_tmap(&m, base, rows, ld_bytes, box_rows));
       it = tmaps.emplace(key, m).first;
     }
     *out = &it->second;
@@ -264,23 +237,25 @@ struct GemmEngine {
     return n >= 256 ? 256 : ((n + 31) / 32) * 32;
   }
 
+  template <int FMT>
+  int launch_fmt(int halves, const cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
+                 const EpilogueParams& ep) {
+    if (halves == 2) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<FMT, 2>, ta, tb, s, ep));
+    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<FMT, 1>, ta, tb, s, ep));
+    return ZETT_OK;
+  }
+
   int launch(const GemmArgs& g, cudaStream_t stream) {
     EpilogueParams ep = g.ep;
     ep.stream_f32 = stream_out ? 1 : 0;
-    if (g.k % 8 != 0) return fail(ZETT_ERR_INVALID, "GEMM K must be a multiple of 8");
+    if (g.k % 8 != 0 || g.n % 8 != 0) return fail(ZETT_ERR_INVALID, "GEMM N and K must be multiples of 8");
+    const long long ld = operand_ld_bytes(fmt, g.k);
+    if (g.a_ld != ld || g.w_ld != ld) return fail(ZETT_ERR_INVALID, "GEMM operand line count does not match K");
     ++launches;
-    const int n_planes = n_terms == 3 ? 2 : 1;
-    const bool f8 = n_terms == 2;
-    if (f8 && (!g.a_q || !g.w_q)) return fail(ZETT_ERR_INVALID, "fp8 planes missing");
-    if (f8 && g.k % 64 != 0) return fail(ZETT_ERR_INVALID, "split_terms = 2 needs every GEMM K (n_embd, hidden, intermediate sizes) to be a multiple of 64");
-    if (f8) block_k = 64;  // the fp8 planes are interleaved per 64 K-elements
     if (impl == 3) {
       SimtGemmParams s{};
-      s.a0 = g.a; s.a1 = n_planes == 2 ? g.a + g.a_plane_stride : nullptr;
-      s.w0 = g.w; s.w1 = n_planes == 2 ? g.w + g.w_plane_stride : nullptr;
-      s.aq = f8 ? g.a_q : nullptr;
-      s.wq = f8 ? g.w_q : nullptr;
-      s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k; s.split_fmt = split_fmt;
+      s.a = g.a; s.a_ld = g.a_ld; s.w = g.w; s.w_ld = g.w_ld;
+      s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k; s.fmt = fmt;
       dim3 grid((g.n + 31) / 32, (g.m_host + 127) / 128);
       if (grid.y == 0 || grid.x == 0) return ZETT_OK;
       ZETT_TRY(time_mark(stream));
@@ -289,87 +264,80 @@ struct GemmEngine {
       ZETT_TRY(time_mark(stream));
       return ZETT_OK;
     }
-    const int cg = impl == 1 ? 1 : 2;
-    const int cp = impl == 4 ? 2 : 1;   // CTA pairs per cluster
     GemmShape s{};
-    s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n; s.k = g.k;
+    s.m_host = g.m_host; s.m_dev = g.m_dev; s.n = g.n;
+    s.k_lines = static_cast<int>(ld / 128);
     s.block_n = pick_block_n(g.n);
-    s.n_halves = 1;
-    if (impl == 5 && s.block_n == 256 && g.n % 512 == 0 && g.k >= 4096) {
-      // 256 x 512 tiles pay when the main loop is long enough to dwarf the exposed epilogue (K >= 4096) and the coarser
-      // tiles still fill whole waves of CTA pairs (a data-dependent M is taken at half its bound, the usual fill)
+    int halves = 1;
+    if (impl == 5 && s.block_n == 256 && g.n % 512 == 0 && g.k >= wide_min_k) {
+      // 256 x 512 tiles pay when the main loop is long enough to dwarf the exposed epilogue and the coarser tiles still
+      // fill whole waves of CTA pairs (a data-dependent M is taken at half its bound, the usual fill)
       const long long m_est = g.m_dev ? std::max(1, g.m_host / 2) : g.m_host;
       const long long tiles = ((m_est + 255) / 256) * (g.n / 512), pairs = std::max(1, dev.num_sms / 2);
       const long long waves = (tiles + pairs - 1) / pairs;
-      if (tiles * 10 >= waves * pairs * 9) s.n_halves = 2;
+      if (tiles * 10 >= waves * pairs * 9) halves = 2;
     }
-    s.n_terms = n_terms; s.n_planes = n_planes; s.f8 = f8 ? 1 : 0; s.mma_mask = mma_mask;
     s.hint_a = hint_a; s.hint_b = hint_b;
-    const int load_n = s.block_n / cg;
-    s.block_k = block_k;
-    s.a_plane_bytes = kBlockM * block_k * 2;
-    s.b_plane_bytes = static_cast<uint32_t>(load_n) * s.n_halves * block_k * 2;
-    s.a8_bytes = f8 ? kBlockM * 128 : 0;
-    s.b8_bytes = f8 ? static_cast<uint32_t>(load_n) * s.n_halves * 128 : 0;
-    s.stage_bytes = n_planes * (s.a_plane_bytes + s.b_plane_bytes) + s.a8_bytes + s.b8_bytes;
-    s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack) / static_cast<int>(s.stage_bytes));
+    const int load_n = s.block_n / 2;
+    s.stage_bytes = kABytes + static_cast<uint32_t>(load_n) * halves * 128u;
+    s.num_stages = std::min<int>(kMaxStages, (kMaxDynSmem - kGemmSmemSlack - static_cast<int>(kStagingBytes)) / static_cast<int>(s.stage_bytes));
     if (s.num_stages < 2) return fail(ZETT_ERR_INVALID, "GEMM tile does not fit two pipeline stages");
-    // instruction descriptor (kind::f16): D fp32, A/B bf16|fp16, both K-major, N >> 3, M >> 4
-    const uint32_t fmt = split_fmt == kFmtBf16 ? 1u : 0u;
-    const uint32_t shape_bits = (static_cast<uint32_t>(s.block_n >> 3) << 17) | (static_cast<uint32_t>((kBlockM * cg) >> 4) << 24);
-    s.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | shape_bits;
+    // instruction descriptors: D fp32 (bit 4), A / B formats at bits 7 / 10, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t f16 = fmt == kFmtF16F8 ? 0u : 1u;   // kind::f16: 0 = fp16, 1 = bf16
+    const uint32_t shape_bits = (static_cast<uint32_t>(s.block_n >> 3) << 17) | (static_cast<uint32_t>((kBlockM * 2) >> 4) << 24);
+    s.idesc16 = (1u << 4) | (f16 << 7) | (f16 << 10) | shape_bits;
     s.idesc8 = (1u << 4) | (1u << 7) | (1u << 10) | shape_bits;  // kind::f8f6f4: A, B = E5M2 (1), D = F32
-    const CUtensorMap *ta, *tb, *ta8, *tb8;
-    // with two pairs per cluster a CTA fetches half of its W share, one plane per copy (gemm_tcgen05.cuh)
-    ZETT_TRY(tmap(g.a, g.a_rows, g.k, g.a_plane_stride, kBlockM, n_planes, n_planes, &ta));
-    ZETT_TRY(tmap(g.w, g.n, g.k, g.w_plane_stride, load_n * s.n_halves / cp, n_planes, cp == 2 ? 1 : n_planes, &tb));
-    ta8 = ta; tb8 = tb;
-    if (f8) {
-      ZETT_TRY(tmap8(g.a_q, g.a_rows, g.k, kBlockM, &ta8));
-      ZETT_TRY(tmap8(g.w_q, g.n, g.k, load_n * s.n_halves / cp, &tb8));
-    }
-    const int tile_m = kBlockM * cg * cp;
+    const CUtensorMap *ta, *tb;
+    ZETT_TRY(tmap(g.a, g.a_rows, g.a_ld, kBlockM, &ta));
+    ZETT_TRY(tmap(g.w, g.n, g.w_ld, load_n * halves, &tb));
+    const int tile_m = kBlockM * 2;
     const long long m_tiles = (g.m_host + tile_m - 1) / tile_m;
-    const long long n_tiles = (g.n + s.block_n * s.n_halves - 1) / (s.block_n * s.n_halves);
-    // W chunk of <= ~48 MB (4 bytes per element in every multi-plane format) stays in the 126 MB L2 next to the A group
-    const long long w_tile_bytes = static_cast<long long>(s.block_n) * s.n_halves * g.k * (n_terms == 1 ? 2 : 4);
+    const long long n_tiles = (g.n + s.block_n * halves - 1) / (s.block_n * halves);
+    // a W chunk of <= ~48 MB stays in the 126 MB L2 next to the A group
+    const long long w_tile_bytes = static_cast<long long>(s.block_n) * halves * ld;
     s.chunk_n = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, raster_chunk_bytes / std::max<long long>(w_tile_bytes, 1))));
-    s.group_m = std::max(1, raster_group_m / cp);
+    s.group_m = std::max(1, raster_group_m);
     const long long tiles = m_tiles * n_tiles;
     if (tiles == 0) return ZETT_OK;
-    const size_t smem = static_cast<size_t>(s.num_stages) * s.stage_bytes + kGemmSmemSlack;
+    const size_t smem = static_cast<size_t>(s.num_stages) * s.stage_bytes + kStagingBytes + kGemmSmemSlack;
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cg * cp; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    int clusters = dev.num_sms / (cg * cp);
-    if (cp == 2) {
-      // clusters of four must sit inside one GPC: the number that can be co-resident depends on the GPC sizes of this
-      // die, and a persistent grid larger than that would serialise whole clusters behind the others
-      if (max_clusters4 < 0) {
-        cfg.gridDim = dim3((dev.num_sms / 4) * 4);
-        cfg.dynamicSmemBytes = kMaxDynSmem;
-        int n = 0;
-        ZETT_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<2, 2>, &cfg));
-        cfg.dynamicSmemBytes = smem;
-        if (n < 1) return fail(ZETT_ERR_CUDA, "no cluster of four CTAs can be resident on this device");
-        max_clusters4 = n;
-        if (getenv("ZETT_VERBOSE")) fprintf(stderr, "[zett] co-resident clusters of 4: %d (of %d SMs)\n", n, dev.num_sms);
-      }
-      clusters = std::min(clusters, max_clusters4);
-    }
-    const int ctas = static_cast<int>(std::min<long long>(clusters, tiles)) * cg * cp;
-    cfg.gridDim = dim3(ctas);
+    const int pairs = static_cast<int>(std::min<long long>(dev.num_sms / 2, tiles));
+    cfg.gridDim = dim3(pairs * 2);
+    s.prof = (prof_dev && pairs * 2 <= 256) ? prof_dev : nullptr;
+    if (s.prof) ZETT_CUDA(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 256 * kProfSlots, stream));
     ZETT_TRY(time_mark(stream));
-    if (cg == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1, 1>, *ta, *tb, *ta8, *tb8, s, ep));
-    else if (cp == 1) ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 1>, *ta, *tb, *ta8, *tb8, s, ep));
-    else ZETT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2, 2>, *ta, *tb, *ta8, *tb8, s, ep));
+    if (fmt == kFmtF16F8) ZETT_TRY(launch_fmt<kFmtF16F8>(halves, cfg, *ta, *tb, s, ep));
+    else if (fmt == kFmtBf16x3) ZETT_TRY(launch_fmt<kFmtBf16x3>(halves, cfg, *ta, *tb, s, ep));
+    else ZETT_TRY(launch_fmt<kFmtBf16x1>(halves, cfg, *ta, *tb, s, ep));
     ZETT_TRY(time_mark(stream));
+    last_halves = halves; last_stages = s.num_stages; last_ctas = pairs * 2; last_block_n = s.block_n;
     return ZETT_OK;
+  }
+  int last_halves = 0, last_stages = 0, last_ctas = 0, last_block_n = 0;
+
+  // after a synchronise: the stall picture of the last launch, averaged over the CTAs (ZETT_GEMM_PROF=1)
+  std::string prof_report() {
+    if (!prof_dev || last_ctas == 0) return "";
+    std::vector<unsigned long long> host(static_cast<size_t>(last_ctas) * kProfSlots);
+    if (cudaMemcpy(host.data(), prof_dev, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return "";
+    double sum[kProfSlots] = {0};
+    for (int c = 0; c < last_ctas; ++c)
+      for (int k = 0; k < kProfSlots; ++k) sum[k] += static_cast<double>(host[static_cast<size_t>(c) * kProfSlots + k]);
+    char buf[512];
+    const double n = last_ctas, nl = std::max(1, last_ctas / 2);
+    snprintf(buf, sizeof buf,
+             "{\"halves\": %d, \"stages\": %d, \"block_n\": %d, \"ctas\": %d, \"cycles_total\": %.0f, \"producer_wait_empty\": %.0f, "
+             "\"mma_wait_full\": %.0f, \"mma_wait_acc\": %.0f, \"epi_wait_acc\": %.0f, \"epi_busy\": %.0f, \"tiles_per_cta\": %.1f}",
+             last_halves, last_stages, last_block_n, last_ctas, sum[0] / n, sum[1] / n, sum[2] / nl, sum[3] / nl, sum[4] / n, sum[5] / n,
+             sum[6] / n);
+    return buf;
   }
 };
 
@@ -395,19 +363,12 @@ __global__ void fill_f32_kernel(float* x, long long n, long long ld, float v) {
     x[i * ld] = v;
 }
 
-// ---- debugging aid (ZETT_DEBUG=1): per-stage statistics of every output buffer, synchronising after each launch ------
-__global__ void debug_stats_kernel(const void* x, int is16, int fmt, long long rows, long long cols, long long ld, double* out) {
+// ---- debugging aid (ZETT_DEBUG=1): per-stage statistics of every fp32 output buffer, synchronising after each launch -
+__global__ void debug_stats_kernel(const float* x, long long rows, long long cols, long long ld, double* out) {
   double bad = 0, sum = 0;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * cols;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / cols, c = i % cols;
-    float v;
-    if (is16) {
-      const uint16_t u = static_cast<const uint16_t*>(x)[r * ld + c];
-      v = fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(u)) : __half2float(__ushort_as_half(u));
-    } else {
-      v = static_cast<const float*>(x)[r * ld + c];
-    }
+    const float v = x[(i / cols) * ld + i % cols];
     if (isfinite(v)) sum += fabsf(v); else bad += 1;
   }
   atomicAdd(out, bad);
@@ -420,8 +381,8 @@ bool debug_enabled() {
   return on == 1;
 }
 
-void debug_report(const char* name, const void* x, int is16, int fmt, long long rows, const int* rows_dev, long long cols,
-                  long long ld, cudaStream_t stream) {
+void debug_report(const char* name, const float* x, long long rows, const int* rows_dev, long long cols, long long ld,
+                  cudaStream_t stream) {
   if (!debug_enabled() || !x) return;
   cudaError_t e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) { fprintf(stderr, "[zett debug] %-28s kernel fault: %s\n", name, cudaGetErrorString(e)); return; }
@@ -429,12 +390,12 @@ void debug_report(const char* name, const void* x, int is16, int fmt, long long 
   double* d = nullptr;
   cudaMalloc(&d, 2 * sizeof(double));
   cudaMemset(d, 0, 2 * sizeof(double));
-  if (rows * cols > 0) debug_stats_kernel<<<256, 256, 0, stream>>>(x, is16, fmt, rows, cols, ld, d);
+  if (rows * cols > 0) debug_stats_kernel<<<256, 256, 0, stream>>>(x, rows, cols, ld, d);
   double hst[2] = {0, 0};
   cudaMemcpy(hst, d, sizeof hst, cudaMemcpyDeviceToHost);
   cudaFree(d);
-  fprintf(stderr, "[zett debug] %-28s %s rows=%lld cols=%lld nonfinite=%.0f mean|x|=%.6g\n", name, is16 ? "p0 " : "f32", rows,
-          cols, hst[0], rows * cols > 0 ? hst[1] / (static_cast<double>(rows) * cols - hst[0] + 1e-30) : 0.0);
+  fprintf(stderr, "[zett debug] %-28s rows=%lld cols=%lld nonfinite=%.0f mean|x|=%.6g\n", name, rows, cols, hst[0],
+          rows * cols > 0 ? hst[1] / (static_cast<double>(rows) * cols - hst[0] + 1e-30) : 0.0);
 }
 
 struct Staged {
@@ -447,11 +408,18 @@ struct Staged {
   }
 };
 
+// nn.Linear in the engine's operand format.  The fp32 originals stay on the device (`master`, one per stacked part) so
+// that the handle can switch operand format without the caller (zett_hn_set_split_terms: the fallback when an activation
+// leaves fp16's range).
 struct LinearW {
-  uint16_t* planes = nullptr;  // [2, n, k]
+  uint8_t* op = nullptr;       // operand lines [n, ld bytes]
+  long long ld = 0;
   float* bias = nullptr;       // [n]
+  float* inv_scale = nullptr;  // [n] inverse row scales (kFmtF16F8), else nullptr
+  float* inv_scale_buf = nullptr;
   int n = 0, k = 0;
-  long long plane_stride() const { return static_cast<long long>(n) * k; }
+  std::vector<float*> master;  // fp32 [n_each, k] per part
+  int n_each = 0;
 };
 
 struct Projector {  // ProjectorBlock
@@ -464,8 +432,17 @@ struct EncoderLayer {
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
 };
 
+// an activation buffer in operand-line form: `rows` rows of K = `k` elements
+struct OpBuf {
+  uint8_t* base = nullptr;
+  long long rows = 0;
+  int k = 0;
+  long long ld = 0;
+};
+
 struct Workspace {
   long long rows_cap = 0;
+  int fmt = -1;                // operand format the OpBufs were sized for
   std::vector<void*> allocs;
   size_t bytes = 0;
   // pack metadata
@@ -476,14 +453,15 @@ struct Workspace {
   long long uniq_cap = 0;
   unsigned char* tok2_valid = nullptr;
   // position-indexed buffers
-  uint16_t *P_E = nullptr, *PH_a = nullptr, *PH_b = nullptr, *PI = nullptr;
+  OpBuf P_E, PH_a, PH_b, PI;
   float *F1 = nullptr, *F2 = nullptr, *F3 = nullptr, *F4 = nullptr;
   // row-indexed (compact) buffers
   float *CX0 = nullptr, *CQ0 = nullptr, *CZ = nullptr, *CX1 = nullptr, *CH0 = nullptr;
-  uint16_t *CPX0 = nullptr, *CPC = nullptr, *CPX1 = nullptr, *CPH0 = nullptr, *CPG = nullptr;
+  OpBuf CPX0, CPC, CPX1, CPH0, CPG;
 };
 
 constexpr int kMaxPassSlots = 4096;
+enum : int { kFlagBadId = 0, kFlagSaturated = 1, kFlagSlots = 4 };   // sticky device words of a handle
 
 }  // namespace
 
@@ -503,11 +481,19 @@ struct zett_hn {
         *oscale_w = nullptr, *oscale_b = nullptr, *type0 = nullptr, *pos_table = nullptr, *emb_ln_w = nullptr,
         *emb_ln_b = nullptr, *lang_pre = nullptr, *biasproj_w = nullptr, *biasproj_b = nullptr;
   Workspace ws;
+  unsigned int* flags = nullptr;   // [kFlagSlots] device: sticky bad-id flag, count of operand values outside fp16's range
   // statistics
   long long passes = 0;
   zett_hn_stats stats{};
   double coef_t1 = 0, coef_t2 = 0, coef_rows = 0, coef_u = 0, coef_p = 0;  // FLOPs per surface position / encoder position / row / distinct id / distinct pair
   bool dedup_pairs = true;     // first encoder layer: LayerNorm + query/key/value once per distinct (id, position) pair
+  bool auto_terms = true;      // split_terms was left at 0: the caller accepts a fallback to the bf16 split
+  std::vector<LinearW*> linears() {
+    std::vector<LinearW*> v = {&in_proj0, &in_proj1.dense1, &in_proj1.dense2, &head_in.dense1, &head_in.dense2, &out_in};
+    if (head_out.dense1.op) { v.push_back(&head_out.dense1); v.push_back(&head_out.dense2); v.push_back(&out_out); }
+    for (auto& l : layers) { v.push_back(&l.qkv); v.push_back(&l.attn_out); v.push_back(&l.inter); v.push_back(&l.out); }
+    return v;
+  }
 };
 
 namespace {
@@ -534,20 +520,36 @@ void free_workspace(zett_hn* h) {
 size_t workspace_bytes_for(const zett_hn* h, long long rows) {
   const long long t1 = rows * h->L, t2 = rows * h->S;
   const long long H = h->H, I = h->I, E = h->E;
+  const int fmt = h->gemm.fmt;
   size_t b = 0;
   const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
   b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 6 * t1 + rows + t2 + 2 * n_ids) + t2;
   b += sizeof(int) * (2 * n_ids * h->L + 2 * (t1 + 1) + t2 + rows);  // distinct (id, position) pairs, per-row counts
-  b += 2ull * 2 * std::min<long long>(t1, n_ids) * E;  // P_E
-  b += 2ull * 2 * t2 * H * 2;             // PH_a, PH_b
-  b += 2ull * 2 * t2 * I;                 // PI
+  b += static_cast<size_t>(std::min<long long>(t1, n_ids) * operand_ld_bytes(fmt, E));  // P_E
+  b += static_cast<size_t>(2 * t2 * operand_ld_bytes(fmt, H));                          // PH_a, PH_b
+  b += static_cast<size_t>(t2 * operand_ld_bytes(fmt, I));                              // PI
   b += 4ull * t2 * H * 3 + 4ull * t2 * 3 * H;  // F1..F3, F4
-  b += 4ull * rows * H * 5 + 2ull * 2 * rows * H * 4 + 2ull * 2 * rows * I;
+  b += 4ull * rows * H * 5 + static_cast<size_t>(rows * (4 * operand_ld_bytes(fmt, H) + operand_ld_bytes(fmt, I)));
   return b + 64 * 256;
 }
 
+// operand-line buffer, zeroed once: the padding of every row's last line must read as zeros (operand.cuh)
+int alloc_opbuf(zett_hn* h, OpBuf* b, long long rows, int k) {
+  b->rows = rows; b->k = k; b->ld = operand_ld_bytes(h->gemm.fmt, k);
+  ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&b->base), static_cast<size_t>(rows * b->ld), true));
+  ZETT_CUDA(cudaMemset(b->base, 0, static_cast<size_t>(rows * b->ld)));
+  return ZETT_OK;
+}
+
+OperandOut out_of(const zett_hn* h, const OpBuf& b) {
+  OperandOut o;
+  o.base = b.base; o.ld_bytes = b.ld; o.fmt = h->gemm.fmt; o.sat = h->gemm.fmt == kFmtF16F8 ? h->flags + kFlagSaturated : nullptr;
+  return o;
+}
+OperandOut no_operand() { return OperandOut{nullptr, 0, 0, nullptr}; }
+
 int ensure_workspace(zett_hn* h, long long rows) {
-  if (h->ws.rows_cap >= rows) return ZETT_OK;
+  if (h->ws.rows_cap >= rows && h->ws.fmt == h->gemm.fmt) return ZETT_OK;
   free_workspace(h);
   Workspace& w = h->ws;
   const long long t1 = rows * h->L, t2 = rows * h->S;
@@ -575,10 +577,10 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.pair_u, t1 + 1);
   WS_ALLOC(w.pair_pos, t1 + 1);
   WS_ALLOC(w.enc_pair, t2);
-  WS_ALLOC(w.P_E, 2 * w.uniq_cap * E);
-  WS_ALLOC(w.PH_a, 2 * t2 * H);
-  WS_ALLOC(w.PH_b, 2 * t2 * H);
-  WS_ALLOC(w.PI, 2 * t2 * I);
+  ZETT_TRY(alloc_opbuf(h, &w.P_E, w.uniq_cap, static_cast<int>(E)));
+  ZETT_TRY(alloc_opbuf(h, &w.PH_a, t2, static_cast<int>(H)));
+  ZETT_TRY(alloc_opbuf(h, &w.PH_b, t2, static_cast<int>(H)));
+  ZETT_TRY(alloc_opbuf(h, &w.PI, t2, static_cast<int>(I)));
   WS_ALLOC(w.F1, t2 * H);
   WS_ALLOC(w.F2, t2 * H);
   WS_ALLOC(w.F3, t2 * H);
@@ -588,14 +590,15 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.CZ, rows * H);
   WS_ALLOC(w.CX1, rows * H);
   WS_ALLOC(w.CH0, rows * H);
-  WS_ALLOC(w.CPX0, 2 * rows * H);
-  WS_ALLOC(w.CPC, 2 * rows * H);
-  WS_ALLOC(w.CPX1, 2 * rows * H);
-  WS_ALLOC(w.CPH0, 2 * rows * H);
-  WS_ALLOC(w.CPG, 2 * rows * I);
+  ZETT_TRY(alloc_opbuf(h, &w.CPX0, rows, static_cast<int>(H)));
+  ZETT_TRY(alloc_opbuf(h, &w.CPC, rows, static_cast<int>(H)));
+  ZETT_TRY(alloc_opbuf(h, &w.CPX1, rows, static_cast<int>(H)));
+  ZETT_TRY(alloc_opbuf(h, &w.CPH0, rows, static_cast<int>(H)));
+  ZETT_TRY(alloc_opbuf(h, &w.CPG, rows, static_cast<int>(I)));
 #undef WS_ALLOC
   ZETT_CUDA(cudaMemset(w.counts_all, 0, sizeof(int) * kMaxPassSlots * kCntSlots));
   w.rows_cap = rows;
+  w.fmt = h->gemm.fmt;
   return ZETT_OK;
 }
 
@@ -620,12 +623,25 @@ int take_vector(zett_hn* h, const std::string& name, std::vector<int64_t> shape,
   return ZETT_OK;
 }
 
-int split_into(zett_hn* h, const float* src, long long rows, long long k, uint16_t* base, long long off0, long long plane_stride) {
-  const long long n4 = rows * k / 4;
-  const int blocks = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8));
-  split_planes_kernel<<<std::max(blocks, 1), 256>>>(src, n4, base, h->gemm.n_terms != 1 ? base + plane_stride : nullptr, off0,
-                                                    h->gemm.split_fmt, true);
-  ZETT_CUDA(cudaGetLastError());
+// (re)build the operand lines of a Linear from its fp32 masters, in the engine's current format
+int split_linear(zett_hn* h, LinearW* lw) {
+  const int fmt = h->gemm.fmt;
+  const long long ld = operand_ld_bytes(fmt, lw->k);
+  if (lw->op == nullptr || lw->ld != ld) {
+    if (lw->op) cudaFree(lw->op);
+    lw->ld = ld;
+    ZETT_CUDA(cudaMalloc(&lw->op, static_cast<size_t>(lw->n) * ld));
+  }
+  ZETT_CUDA(cudaMemset(lw->op, 0, static_cast<size_t>(lw->n) * ld));
+  lw->inv_scale = fmt == kFmtF16F8 ? lw->inv_scale_buf : nullptr;
+  OperandOut o;
+  o.base = lw->op; o.ld_bytes = ld; o.fmt = fmt; o.sat = fmt == kFmtF16F8 ? h->flags + kFlagSaturated : nullptr;
+  for (size_t i = 0; i < lw->master.size(); ++i) {
+    const int blocks = std::min(lw->n_each, 148 * 16);
+    split_rows_kernel<<<std::max(blocks, 1), 256>>>(lw->master[i], lw->n_each, lw->k, o, static_cast<long long>(i) * lw->n_each, true,
+                                                    lw->inv_scale);
+    ZETT_CUDA(cudaGetLastError());
+  }
   return ZETT_OK;
 }
 
@@ -633,25 +649,25 @@ int split_into(zett_hn* h, const float* src, long long rows, long long k, uint16
 int make_linear(zett_hn* h, const std::vector<std::string>& prefixes, int n_each, int k, LinearW* out) {
   const int parts = static_cast<int>(prefixes.size());
   out->n = n_each * parts;
+  out->n_each = n_each;
   out->k = k;
-  if ((static_cast<long long>(n_each) * k) % 4 != 0) return fail(ZETT_ERR_INVALID, "Linear size must be a multiple of 4");
-  ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&out->planes), sizeof(uint16_t) * 2ull * out->n * k, false));
+  if (k % 8 != 0 || n_each % 8 != 0) return fail(ZETT_ERR_INVALID, "Linear sizes must be multiples of 8");
   ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&out->bias), sizeof(float) * out->n, false));
+  ZETT_TRY(dev_alloc(h, reinterpret_cast<void**>(&out->inv_scale_buf), sizeof(float) * out->n, false));
   for (int i = 0; i < parts; ++i) {
     float *w, *b;
     ZETT_TRY(staged_get(h, prefixes[i] + ".weight", {n_each, k}, &w));
     ZETT_TRY(staged_get(h, prefixes[i] + ".bias", {n_each}, &b));
-    ZETT_TRY(split_into(h, w, n_each, k, out->planes, static_cast<long long>(i) * n_each * k, out->plane_stride()));
     ZETT_CUDA(cudaMemcpy(out->bias + static_cast<long long>(i) * n_each, b, sizeof(float) * n_each, cudaMemcpyDeviceToDevice));
+    out->master.push_back(w);          // kept: the handle can re-split into another operand format
+    h->owned.push_back(w);
+    h->staged.erase(prefixes[i] + ".weight");
+    auto it = h->staged.find(prefixes[i] + ".bias");
+    cudaFree(it->second.dev);
+    h->staged.erase(it);
   }
+  ZETT_TRY(split_linear(h, out));
   ZETT_CUDA(cudaDeviceSynchronize());
-  for (int i = 0; i < parts; ++i) {
-    for (const char* leaf : {".weight", ".bias"}) {
-      auto it = h->staged.find(prefixes[i] + leaf);
-      cudaFree(it->second.dev);
-      h->staged.erase(it);
-    }
-  }
   return ZETT_OK;
 }
 
@@ -663,13 +679,9 @@ int make_projector(zett_hn* h, const std::string& prefix, Projector* p) {
   return ZETT_OK;
 }
 
-// second half of an operand buffer: the lo plane (16-bit split) or the two fp8 planes (kFmtF16F8); none in single-pass mode
-uint16_t* plane1(uint16_t* p0, long long stride, const zett_hn* h) { return h->gemm.n_terms != 1 ? p0 + stride : nullptr; }
-
 int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
   if (max_rows <= 0) return ZETT_OK;
   p.H = h->H;
-  p.split_fmt = h->gemm.split_fmt;
   const int h4 = h->H / 4;
   if (h4 <= 32 * kLnWarpVec) {  // one warp per row, eight rows per block
     const int grid = static_cast<int>(std::min<long long>((max_rows + 7) / 8, 148LL * 8));
@@ -682,10 +694,7 @@ int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
   }
   ZETT_CUDA(cudaGetLastError());
   ++h->gemm.launches;
-  if (debug_enabled() && !p.out_index) {
-    debug_report("layernorm", p.out_f32, 0, 0, p.n_host, p.n_dev, h->H, h->H, stream);
-    debug_report("layernorm", p.out_p0, 1, p.split_fmt, p.n_host, p.n_dev, h->H, h->H, stream);
-  }
+  if (debug_enabled() && !p.out_index) debug_report("layernorm", p.out_f32, p.n_host, p.n_dev, h->H, h->H, stream);
   return ZETT_OK;
 }
 
@@ -713,26 +722,26 @@ int count_slot(MClass m) {
   return m == kMSurface ? kCntSurface : (m == kMEncoder ? kCntEncoder : (m == kMPairs ? kCntPairs : kCntUnique));
 }
 
-// One Linear layer through the GEMM engine.  `a` / `out_*` are plane-0 pointers; `cap` = rows the buffers hold.
-int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const uint16_t* a, long long cap, MClass mclass,
-               int m_rows, const int* counts, int act, float* out_f32, long long ld_f32, uint16_t* out_p0,
-               long long out_cap, const float* col_scale, const float* col_shift, cudaStream_t stream,
-               const float* residual = nullptr) {
+// One Linear layer through the GEMM engine: rows [row_off, row_off + n_rows_w) of `w` applied to the operand buffer `a`;
+// results go to fp32 (`out_f32`, nullable) and / or operand lines (`out_op`, nullable).
+int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const OpBuf& a, MClass mclass, int m_rows,
+               const int* counts, int act, float* out_f32, long long ld_f32, const OpBuf* out_op, const float* col_scale,
+               const float* col_shift, cudaStream_t stream, const float* residual = nullptr) {
+  if (a.k != w.k) return fail(ZETT_ERR_STATE, "internal: operand buffer width does not match the Linear");
+  if (out_op && out_op->k != n_rows_w) return fail(ZETT_ERR_STATE, "internal: output operand buffer width does not match the Linear");
   GemmArgs g;
-  g.a = a; g.a_rows = cap; g.a_plane_stride = cap * w.k;
-  g.w = w.planes + static_cast<long long>(row_off) * w.k; g.w_plane_stride = w.plane_stride();
-  g.a_q = reinterpret_cast<const uint8_t*>(a + g.a_plane_stride);
-  g.w_q = reinterpret_cast<const uint8_t*>(w.planes + w.plane_stride()) + 2ll * row_off * w.k;
+  g.a = a.base; g.a_rows = a.rows; g.a_ld = a.ld;
+  g.w = w.op + static_cast<long long>(row_off) * w.ld; g.w_ld = w.ld;
   g.n = n_rows_w; g.k = w.k;
   if (mclass == kMRows) { g.m_host = m_rows; g.m_dev = nullptr; }
-  else { g.m_host = static_cast<int>(cap); g.m_dev = counts + count_slot(mclass); }
+  else { g.m_host = static_cast<int>(a.rows); g.m_dev = counts + count_slot(mclass); }
   g.ep.bias = w.bias + row_off;
+  g.ep.w_scale = w.inv_scale ? w.inv_scale + row_off : nullptr;
   g.ep.act = act;
   g.ep.col_scale = col_scale; g.ep.col_shift = col_shift;
   g.ep.residual = residual; g.ep.ld_res = n_rows_w;  // residual stream rows are [*, n]; added after the activation
   g.ep.out_f32 = out_f32; g.ep.ld_out = ld_f32;
-  g.ep.out_p0 = out_p0; g.ep.out_p1 = out_p0 ? plane1(out_p0, out_cap * n_rows_w, h) : nullptr; g.ep.ld_split = n_rows_w;
-  g.ep.split_fmt = h->gemm.split_fmt;
+  g.ep.out_op = out_op ? out_of(h, *out_op) : no_operand();
   const double f = 2.0 * n_rows_w * w.k;
   if (mclass == kMSurface) h->coef_t1 += f; else if (mclass == kMEncoder) h->coef_t2 += f;
   else if (mclass == kMUnique) h->coef_u += f; else if (mclass == kMPairs) h->coef_p += f; else h->coef_rows += f;
@@ -740,24 +749,22 @@ int run_linear(zett_hn* h, const LinearW& w, int row_off, int n_rows_w, const ui
   if (debug_enabled()) {
     char name[64];
     snprintf(name, sizeof name, "gemm n=%d k=%d off=%d", n_rows_w, w.k, row_off);
-    debug_report(name, out_f32, 0, 0, g.m_host, g.m_dev, n_rows_w, ld_f32, stream);
-    debug_report(name, out_p0, 1, h->gemm.split_fmt, g.m_host, g.m_dev, n_rows_w, n_rows_w, stream);
+    debug_report(name, out_f32, g.m_host, g.m_dev, n_rows_w, ld_f32, stream);
   }
   return ZETT_OK;
 }
 
-// ProjectorBlock + LayerNorm(h + x) on `cap`-row buffers: x (fp32 xf, planes xp) -> planes/f32 out
-int run_projector(zett_hn* h, const Projector& pb, const uint16_t* xp, const float* xf, long long cap, MClass mclass,
-                  int m_rows, const int* counts, uint16_t* pg, float* z, LnParams ln_out, cudaStream_t stream) {
-  ZETT_TRY(run_linear(h, pb.dense1, 0, h->I, xp, cap, mclass, m_rows, counts, kActGeluTanh, nullptr, 0, pg, cap, nullptr,
-                      nullptr, stream));
-  ZETT_TRY(run_linear(h, pb.dense2, 0, h->H, pg, cap, mclass, m_rows, counts, kActGeluTanh, z, h->H, nullptr, 0, nullptr,
-                      nullptr, stream, xf));  // z = gelu(dense2(.)) + x, the residual rides in the GEMM epilogue
+// ProjectorBlock + LayerNorm(h + x) on operand buffer xp / fp32 xf -> whatever `ln_out` names
+int run_projector(zett_hn* h, const Projector& pb, const OpBuf& xp, const float* xf, MClass mclass, int m_rows, const int* counts,
+                  const OpBuf& pg, float* z, LnParams ln_out, cudaStream_t stream) {
+  ZETT_TRY(run_linear(h, pb.dense1, 0, h->I, xp, mclass, m_rows, counts, kActGeluTanh, nullptr, 0, &pg, nullptr, nullptr, stream));
+  ZETT_TRY(run_linear(h, pb.dense2, 0, h->H, pg, mclass, m_rows, counts, kActGeluTanh, z, h->H, nullptr, nullptr, nullptr, stream,
+                      xf));  // z = gelu(dense2(.)) + x, the residual rides in the GEMM epilogue
   ln_out.a = z; ln_out.lda = h->H; ln_out.res = nullptr;
   ln_out.gamma = pb.ln_w; ln_out.beta = pb.ln_b; ln_out.eps = 1e-6f;
   if (mclass == kMRows) { ln_out.n_dev = nullptr; ln_out.n_host = m_rows; }
   else { ln_out.n_dev = counts + count_slot(mclass); ln_out.n_host = 0; }
-  return launch_ln(h, ln_out, mclass == kMRows ? m_rows : cap, stream);
+  return launch_ln(h, ln_out, mclass == kMRows ? m_rows : xp.rows, stream);
 }
 
 int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, long long v0_rows, int lang_index,
@@ -765,20 +772,19 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
                  cudaStream_t stream) {
   Workspace& w = h->ws;
   const int H = h->H, I = h->I, D = h->D, E = h->E, L = h->L, S = h->S;
-  const long long cap1 = w.rows_cap * L, cap2 = w.rows_cap * S, capr = w.rows_cap;
+  (void)I; (void)S;
+  const long long cap1 = w.rows_cap * L, cap2 = w.rows_cap * S;
   const bool lang = h->cfg.hn_embed_lang_id != 0;
   const int n_layers = h->cfg.hn_n_layers;
   int* counts = w.counts_all + (h->passes % kMaxPassSlots) * kCntSlots;
-  const int fmt = h->gemm.split_fmt;
   h->coef_t1 = h->coef_t2 = h->coef_rows = h->coef_u = h->coef_p = 0;
-  const long long capu = w.uniq_cap;
 
   // ---- pack ------------------------------------------------------------------------------------------------------
   ZETT_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * kCntSlots, stream));
   ZETT_CUDA(cudaMemsetAsync(w.id_claim, 0x7F, sizeof(int) * (static_cast<size_t>(h->cfg.original_vocab_size) + h->n_fallback), stream));
   PackParams pp{};
   pp.ids = ids; pp.n_rows = rows; pp.L = L; pp.pad_id = h->cfg.pad_token_id; pp.v0 = h->cfg.original_vocab_size;
-  pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.counts = counts;
+  pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.counts = counts; pp.sticky_bad = h->flags + kFlagBadId;
   pp.row_cnt = w.row_cnt; pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_id = w.tok_id; pp.tok_pos = w.tok_pos;
   pp.tok_enc = w.tok_enc; pp.tok1_row = w.tok1_row; pp.lang_enc = w.lang_enc; pp.tok2_row = w.tok2_row; pp.tok2_valid = w.tok2_valid;
   pp.id_claim = w.id_claim; pp.id_slot = w.id_slot; pp.uniq_src = w.uniq_src; pp.tok_u = w.tok_u;
@@ -800,29 +806,29 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
     h->gemm.launches += 5;
   }
 
-  // ---- gather + in_scaler + split  (modeling_hypernet.py:170-188) ------------------------------------------------
+  // ---- gather + in_scaler + operand lines  (modeling_hypernet.py:170-188) -----------------------------------------
   {
     GatherParams gp{};
     gp.source = source; gp.v0_rows = v0_rows; gp.fallback = h->fallback;
     gp.scale_w = h->in_scale_w; gp.scale_b = h->in_scale_b; gp.tok_src = w.uniq_src; gp.n_tok = counts + kCntUnique;
-    gp.E = E; gp.split_fmt = fmt; gp.out_p0 = w.P_E; gp.out_p1 = plane1(w.P_E, capu * E, h);
+    gp.E = E; gp.out = out_of(h, w.P_E);
     const size_t smem = 2ull * E * 4;
     const int per_sm = std::max<int>(1, std::min<int>(8, 200 * 1024 / static_cast<int>(smem + 64)));
-    const int grid = static_cast<int>(std::min<long long>(std::min<long long>(static_cast<long long>(rows) * L, capu), 148LL * per_sm));
+    const int grid = static_cast<int>(std::min<long long>(std::min<long long>(static_cast<long long>(rows) * L, w.uniq_cap), 148LL * per_sm));
     gather_rescale_kernel<<<grid, kGatherThreads, smem, stream>>>(gp);
     ZETT_CUDA(cudaGetLastError());
     ++h->gemm.launches;
-    debug_report("gather", w.P_E, 1, fmt, 0, counts + kCntUnique, E, E, stream);
   }
 
   // ---- input_projection = Linear(E, H); ProjectorBlock  (modeling_hypernet.py:100-110,189) -----------------------
-  // evaluated once per distinct id of the pass (the result depends on the id only); positions pick their row below
-  ZETT_TRY(run_linear(h, h->in_proj0, 0, H, w.P_E, capu, kMUnique, 0, counts, kActNone, w.F1, H, w.PH_a, capu, nullptr,
-                      nullptr, stream));
+  // evaluated once per distinct id of the pass (the result depends on the id only); positions pick their row below.
+  // PH_b / PI are sized for the encoder packing, which is at least as long as the list of distinct ids.
+  ZETT_TRY(run_linear(h, h->in_proj0, 0, H, w.P_E, kMUnique, 0, counts, kActNone, w.F1, H, &w.PH_b, nullptr, nullptr, stream));
   {
     LnParams ln{};  // U = LN_1e-6(gelu(dense2(gelu(dense1 y))) + y), in place over Z
     ln.out_f32 = w.F2;
-    ZETT_TRY(run_projector(h, h->in_proj1, w.PH_a, w.F1, capu, kMUnique, 0, counts, w.PI, w.F2, ln, stream));
+    ln.out_op = no_operand(); ln.c_op = no_operand();
+    ZETT_TRY(run_projector(h, h->in_proj1, w.PH_b, w.F1, kMUnique, 0, counts, w.PI, w.F2, ln, stream));
   }
   // ---- RobertaEmbeddings: + token_type[0] + position[pos]; LayerNorm 1e-5; scatter into the encoder packing -------
   const bool single_layer = n_layers == 1;
@@ -832,10 +838,11 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
     ln.gamma = h->emb_ln_w; ln.beta = h->emb_ln_b; ln.eps = h->cfg.encoder_layer_norm_eps;
     ln.n_dev = counts + kCntSurface; ln.out_index = w.tok_enc;
     ln.out_f32 = w.F3;
-    if (!pairs) { ln.out_p0 = w.PH_a; ln.out_p1 = plane1(w.PH_a, cap2 * H, h); }  // else: operand rows per distinct pair below
+    ln.out_op = pairs ? no_operand() : out_of(h, w.PH_a);  // with pairs: operand rows per distinct pair below
+    ln.c_op = no_operand();
     if (single_layer) {
       ln.tok_row = w.tok1_row; ln.row_start = w.row_start1;
-      ln.c_f32 = w.CX0; ln.c_p0 = w.CPX0; ln.c_p1 = plane1(w.CPX0, capr * H, h);
+      ln.c_f32 = w.CX0; ln.c_op = out_of(h, w.CPX0);
     }
     ZETT_TRY(launch_ln(h, ln, cap1, stream));
     if (lang) {  // lang-id slot: lang_embedding (position/type pre-subtracted) at position L  (modeling_hypernet.py:192-218)
@@ -845,15 +852,16 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
       ll.gamma = h->emb_ln_w; ll.beta = h->emb_ln_b; ll.eps = h->cfg.encoder_layer_norm_eps;
       ll.n_host = rows; ll.out_index = w.lang_enc;
       ll.out_f32 = w.F3;
-      if (!pairs) { ll.out_p0 = w.PH_a; ll.out_p1 = plane1(w.PH_a, cap2 * H, h); }
+      ll.out_op = pairs ? no_operand() : out_of(h, w.PH_a);
+      ll.c_op = no_operand();
       ZETT_TRY(launch_ln(h, ll, rows, stream));
     }
-    if (pairs) {  // the same LayerNorm once per distinct (id, position) pair -> operand planes of the layer-0 QKV GEMM
+    if (pairs) {  // the same LayerNorm once per distinct (id, position) pair -> operand rows of the layer-0 QKV GEMM
       LnParams lp{};
       lp.a = w.F2; lp.lda = H; lp.in_index = w.pair_u; lp.vec0 = h->type0; lp.table = h->pos_table; lp.table_idx = w.pair_pos;
       lp.gamma = h->emb_ln_w; lp.beta = h->emb_ln_b; lp.eps = h->cfg.encoder_layer_norm_eps;
       lp.n_dev = counts + kCntPairs;
-      lp.out_p0 = w.PH_a; lp.out_p1 = plane1(w.PH_a, cap2 * H, h);
+      lp.out_op = out_of(h, w.PH_a); lp.c_op = no_operand();
       ZETT_TRY(launch_ln(h, lp, cap1 + 1, stream));
       if (lang) {  // pair 0 = the lang-id position (after the launch above, which wrote a placeholder there)
         LnParams ll{};
@@ -861,7 +869,7 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
         ll.table = h->pos_table; ll.table_idx = nullptr; ll.table_const = L;
         ll.gamma = h->emb_ln_w; ll.beta = h->emb_ln_b; ll.eps = h->cfg.encoder_layer_norm_eps;
         ll.n_host = 1;
-        ll.out_p0 = w.PH_a; ll.out_p1 = plane1(w.PH_a, cap2 * H, h);
+        ll.out_op = out_of(h, w.PH_a); ll.c_op = no_operand();
         ZETT_TRY(launch_ln(h, ll, 1, stream));
       }
     }
@@ -874,58 +882,50 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
     const bool last = l == n_layers - 1;
     if (!last) {
       const bool on_pairs = pairs && l == 0;
-      ZETT_TRY(run_linear(h, ly.qkv, 0, 3 * H, w.PH_a, cap2, on_pairs ? kMPairs : kMEncoder, 0, counts, kActNone, w.F4, 3 * H,
-                          nullptr, 0, nullptr, nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.qkv, 0, 3 * H, w.PH_a, on_pairs ? kMPairs : kMEncoder, 0, counts, kActNone, w.F4, 3 * H, nullptr,
+                          nullptr, nullptr, stream));
       AttnParams ap{};
       ap.qkv_index = on_pairs ? w.enc_pair : nullptr;
       ap.q = w.F4; ap.ldq = 3 * H; ap.k = w.F4 + H; ap.ldk = 3 * H; ap.v = w.F4 + 2 * H; ap.ldv = 3 * H;
       ap.row_start = w.row_start2; ap.valid = w.tok2_valid; ap.n_rows = rows; ap.n_heads = h->heads; ap.dh = h->dh;
-      ap.scale = scale; ap.row0_only = 0; ap.out_p0 = w.PH_b; ap.out_p1 = plane1(w.PH_b, cap2 * H, h); ap.ld_out = H;
-      ap.split_fmt = fmt;
+      ap.scale = scale; ap.row0_only = 0; ap.out = out_of(h, w.PH_b);
       ZETT_TRY(launch_attention(h, ap, stream));
-      ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.PH_b, cap2, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, 0, nullptr,
-                          nullptr, stream, w.F3));
+      ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.PH_b, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, nullptr, nullptr, stream,
+                          w.F3));
       LnParams l1{};
       l1.a = w.F2; l1.lda = H; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
-      l1.n_dev = counts + kCntEncoder; l1.out_f32 = w.F1; l1.out_p0 = w.PH_b; l1.out_p1 = plane1(w.PH_b, cap2 * H, h);
+      l1.n_dev = counts + kCntEncoder; l1.out_f32 = w.F1; l1.out_op = out_of(h, w.PH_b); l1.c_op = no_operand();
       ZETT_TRY(launch_ln(h, l1, cap2, stream));
-      ZETT_TRY(run_linear(h, ly.inter, 0, I, w.PH_b, cap2, kMEncoder, 0, counts, kActGeluErf, nullptr, 0, w.PI, cap2, nullptr,
-                          nullptr, stream));
-      ZETT_TRY(run_linear(h, ly.out, 0, H, w.PI, cap2, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, 0, nullptr, nullptr,
-                          stream, w.F1));
+      ZETT_TRY(run_linear(h, ly.inter, 0, I, w.PH_b, kMEncoder, 0, counts, kActGeluErf, nullptr, 0, &w.PI, nullptr, nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.out, 0, H, w.PI, kMEncoder, 0, counts, kActNone, w.F2, H, nullptr, nullptr, nullptr, stream, w.F1));
       LnParams l2{};
       l2.a = w.F2; l2.lda = H; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
-      l2.n_dev = counts + kCntEncoder; l2.out_f32 = w.F3; l2.out_p0 = w.PH_a; l2.out_p1 = plane1(w.PH_a, cap2 * H, h);
+      l2.n_dev = counts + kCntEncoder; l2.out_f32 = w.F3; l2.out_op = out_of(h, w.PH_a); l2.c_op = no_operand();
       if (l == n_layers - 2) {  // the pruned last layer reads position 0 of every row from compact buffers
         l2.tok_row = w.tok2_row; l2.row_start = w.row_start2;
-        l2.c_f32 = w.CX0; l2.c_p0 = w.CPX0; l2.c_p1 = plane1(w.CPX0, capr * H, h);
+        l2.c_f32 = w.CX0; l2.c_op = out_of(h, w.CPX0);
       }
       ZETT_TRY(launch_ln(h, l2, cap2, stream));
     } else {
       // K, V for every position; Q, attention output, MLP only for position 0 of each row (hidden[:, 0], :231-234)
-      ZETT_TRY(run_linear(h, ly.qkv, H, 2 * H, w.PH_a, cap2, kMEncoder, 0, counts, kActNone, w.F4, 2 * H, nullptr, 0, nullptr,
-                          nullptr, stream));
-      ZETT_TRY(run_linear(h, ly.qkv, 0, H, w.CPX0, capr, kMRows, rows, counts, kActNone, w.CQ0, H, nullptr, 0, nullptr,
-                          nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.qkv, H, 2 * H, w.PH_a, kMEncoder, 0, counts, kActNone, w.F4, 2 * H, nullptr, nullptr, nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.qkv, 0, H, w.CPX0, kMRows, rows, counts, kActNone, w.CQ0, H, nullptr, nullptr, nullptr, stream));
       AttnParams ap{};
       ap.q = w.CQ0; ap.ldq = H; ap.k = w.F4; ap.ldk = 2 * H; ap.v = w.F4 + H; ap.ldv = 2 * H;
       ap.row_start = w.row_start2; ap.valid = w.tok2_valid; ap.n_rows = rows; ap.n_heads = h->heads; ap.dh = h->dh;
-      ap.scale = scale; ap.row0_only = 1; ap.out_p0 = w.CPC; ap.out_p1 = plane1(w.CPC, capr * H, h); ap.ld_out = H;
-      ap.split_fmt = fmt;
+      ap.scale = scale; ap.row0_only = 1; ap.out = out_of(h, w.CPC);
       ZETT_TRY(launch_attention(h, ap, stream));
-      ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.CPC, capr, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, 0, nullptr,
-                          nullptr, stream, w.CX0));
+      ZETT_TRY(run_linear(h, ly.attn_out, 0, H, w.CPC, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, nullptr, nullptr, stream,
+                          w.CX0));
       LnParams l1{};
       l1.a = w.CZ; l1.lda = H; l1.gamma = ly.ln1_w; l1.beta = ly.ln1_b; l1.eps = h->cfg.encoder_layer_norm_eps;
-      l1.n_host = rows; l1.out_f32 = w.CX1; l1.out_p0 = w.CPX1; l1.out_p1 = plane1(w.CPX1, capr * H, h);
+      l1.n_host = rows; l1.out_f32 = w.CX1; l1.out_op = out_of(h, w.CPX1); l1.c_op = no_operand();
       ZETT_TRY(launch_ln(h, l1, rows, stream));
-      ZETT_TRY(run_linear(h, ly.inter, 0, I, w.CPX1, capr, kMRows, rows, counts, kActGeluErf, nullptr, 0, w.CPG, capr, nullptr,
-                          nullptr, stream));
-      ZETT_TRY(run_linear(h, ly.out, 0, H, w.CPG, capr, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, 0, nullptr, nullptr,
-                          stream, w.CX1));
+      ZETT_TRY(run_linear(h, ly.inter, 0, I, w.CPX1, kMRows, rows, counts, kActGeluErf, nullptr, 0, &w.CPG, nullptr, nullptr, stream));
+      ZETT_TRY(run_linear(h, ly.out, 0, H, w.CPG, kMRows, rows, counts, kActNone, w.CZ, H, nullptr, nullptr, nullptr, stream, w.CX1));
       LnParams l2{};
       l2.a = w.CZ; l2.lda = H; l2.gamma = ly.ln2_w; l2.beta = ly.ln2_b; l2.eps = h->cfg.encoder_layer_norm_eps;
-      l2.n_host = rows; l2.out_f32 = w.CH0; l2.out_p0 = w.CPH0; l2.out_p1 = plane1(w.CPH0, capr * H, h);
+      l2.n_host = rows; l2.out_f32 = w.CH0; l2.out_op = out_of(h, w.CPH0); l2.c_op = no_operand();
       if (h->cfg.hn_predict_bias) {  // bias_projection(hidden[:, 0])[..., 0]  (:260-261)
         l2.dot_w = h->biasproj_w; l2.dot_b = h->biasproj_b; l2.dot_out = pred_bias; l2.dot_ld = ld_bias;
       }
@@ -943,13 +943,12 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
                       const float* sb_in, const LinearW* proj_out, int off_out, float* dst_out, const float* sw_out,
                       const float* sb_out) -> int {
     LnParams ln{};
-    ln.out_p0 = w.CPX1; ln.out_p1 = plane1(w.CPX1, capr * H, h);
-    ZETT_TRY(run_projector(h, pb, w.CPH0, w.CH0, capr, kMRows, rows, counts, w.CPG, w.CZ, ln, stream));
-    ZETT_TRY(run_linear(h, proj_in, off_in, D, w.CPX1, capr, kMRows, rows, counts, kActNone, dst_in, ld_pred, nullptr, 0, sw_in,
-                        sb_in, stream));
+    ln.out_op = out_of(h, w.CPX1); ln.c_op = no_operand();
+    ZETT_TRY(run_projector(h, pb, w.CPH0, w.CH0, kMRows, rows, counts, w.CPG, w.CZ, ln, stream));
+    ZETT_TRY(run_linear(h, proj_in, off_in, D, w.CPX1, kMRows, rows, counts, kActNone, dst_in, ld_pred, nullptr, sw_in, sb_in, stream));
     if (proj_out)
-      ZETT_TRY(run_linear(h, *proj_out, off_out, D, w.CPX1, capr, kMRows, rows, counts, kActNone, dst_out, ld_pred, nullptr, 0,
-                          sw_out, sb_out, stream));
+      ZETT_TRY(run_linear(h, *proj_out, off_out, D, w.CPX1, kMRows, rows, counts, kActNone, dst_out, ld_pred, nullptr, sw_out, sb_out,
+                          stream));
     return ZETT_OK;
   };
   const bool separate = h->cfg.separate_out_embeddings != 0;
@@ -1017,15 +1016,24 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   int impl = cfg->gemm_impl;
   if (const char* e = getenv("ZETT_GEMM_IMPL")) impl = atoi(e);
   h->gemm.impl = impl == 0 ? 5 : impl;
-  if (h->gemm.impl < 1 || h->gemm.impl > 5) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0..5"); }
+  if (h->gemm.impl != 2 && h->gemm.impl != 3 && h->gemm.impl != 5) { delete h; return fail(ZETT_ERR_INVALID, "gemm_impl must be 0, 2, 3 or 5"); }
   int terms = cfg->split_terms;
-  if (const char* e = getenv("ZETT_SPLIT_TERMS")) terms = atoi(e);
-  // auto: fp16 + two e5m2 correction planes (fewest tensor-pipe cycles inside the 1e-3 budget) when every GEMM K is a
-  // multiple of 64 (its fp8 planes are interleaved per 64 K-elements), else the three-term bf16 split
-  if (terms == 0) terms = (h->E % 64 == 0 && H % 64 == 0 && I % 64 == 0) ? 2 : 3;
-  h->gemm.set_precision(terms);
+  if (const char* e = getenv("ZETT_SPLIT_TERMS")) {
+    terms = atoi(e);
+    fprintf(stderr, "[zett_b200] ZETT_SPLIT_TERMS=%d overrides the configured operand format%s\n", terms,
+            terms == 1 ? " -- ONE bf16 pass does NOT meet the 1e-3 parity budget (probe mode)" : "");
+  }
+  if (terms < 0 || terms > 3) { delete h; return fail(ZETT_ERR_INVALID, "split_terms must be 0..3"); }
+  // auto: fp16 + two e5m2 correction terms (fewest tensor-pipe cycles inside the 1e-3 budget); zett_hn_check reports
+  // ZETT_ERR_RANGE if a value left fp16's range, and zett_hn_set_split_terms(h, 3) switches to the three-term bf16 split
+  h->auto_terms = terms == 0;
+  h->gemm.set_precision(terms == 0 ? 2 : terms);
   h->gemm.read_env();
   if (const char* e = getenv("ZETT_DEDUP_PAIRS")) h->dedup_pairs = atoi(e) != 0;
+  if (cudaMalloc(&h->flags, sizeof(unsigned int) * kFlagSlots) != cudaSuccess || cudaMemset(h->flags, 0, sizeof(unsigned int) * kFlagSlots) != cudaSuccess) {
+    delete h;
+    return fail(ZETT_ERR_CUDA, "cannot allocate the handle's flag words");
+  }
   *out = h;
   return ZETT_OK;
 }
@@ -1191,7 +1199,6 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
     std::vector<int> host(static_cast<size_t>(kMaxPassSlots) * kCntSlots);
     ZETT_CUDA(cudaMemcpy(host.data(), h->ws.counts_all, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
     long long t1 = 0, t2 = 0, rows = 0, uq = 0, pq = 0;
-    int bad = 0;
     for (long long i = 0; i < n_pass; ++i) {
       const long long slot = ((h->passes - 1 - i) % kMaxPassSlots + kMaxPassSlots) % kMaxPassSlots;
       t1 += host[slot * kCntSlots + kCntSurface];
@@ -1199,16 +1206,43 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
       rows += host[slot * kCntSlots + kCntRows];
       uq += host[slot * kCntSlots + kCntUnique];
       pq += host[slot * kCntSlots + kCntPairs];
-      bad |= host[slot * kCntSlots + kCntBadId];
     }
     h->stats.packed_positions = t1;
     h->stats.encoder_positions = t2;
     h->stats.flops_executed = h->coef_t1 * t1 + h->coef_t2 * t2 + h->coef_rows * rows + h->coef_u * uq + h->coef_p * pq;
     h->stats.distinct_ids = uq;
     h->stats.distinct_pairs = pq;
-    if (bad)
-      return fail(ZETT_ERR_INDEX, "surface-form id outside [0, original_vocab_size + max(hn_n_extra_tokens, 1))");
   }
+  // the sticky words cover EVERY forward since the last check (a pipeline of many calls is checked once at its end)
+  unsigned int flags[kFlagSlots] = {0};
+  if (h->flags) {
+    ZETT_CUDA(cudaMemcpy(flags, h->flags, sizeof flags, cudaMemcpyDeviceToHost));
+    if (flags[kFlagBadId] || flags[kFlagSaturated]) ZETT_CUDA(cudaMemset(h->flags, 0, sizeof flags));
+  }
+  h->stats.operand_overflows = flags[kFlagSaturated];
+  if (flags[kFlagBadId])
+    return fail(ZETT_ERR_INDEX, "surface-form id outside [0, original_vocab_size + max(hn_n_extra_tokens, 1))");
+  if (flags[kFlagSaturated])
+    return fail(ZETT_ERR_RANGE, std::to_string(flags[kFlagSaturated]) + " warp(s) produced GEMM operand values outside fp16's range "
+                "(|x| > 65504): the results of this forward are not within the parity budget; call zett_hn_set_split_terms(h, 3) "
+                "and run it again");
+  return ZETT_OK;
+}
+
+int zett_hn_set_split_terms(zett_hn* h, int split_terms) {
+  if (!h) return fail(ZETT_ERR_INVALID, "null handle");
+  if (split_terms < 1 || split_terms > 3) return fail(ZETT_ERR_INVALID, "split_terms must be 1, 2 or 3");
+  if (!h->finalized) return fail(ZETT_ERR_STATE, "zett_hn_set_split_terms before zett_hn_finalize");
+  if (split_terms == h->gemm.n_terms) return ZETT_OK;
+  ZETT_CUDA(cudaSetDevice(h->gemm.dev.device));
+  ZETT_CUDA(cudaDeviceSynchronize());
+  if (split_terms == 1) fprintf(stderr, "[zett_b200] split_terms = 1: ONE bf16 pass does NOT meet the 1e-3 parity budget (probe mode)\n");
+  h->gemm.set_precision(split_terms);
+  h->gemm.tmaps.clear();
+  free_workspace(h);
+  for (LinearW* lw : h->linears()) ZETT_TRY(split_linear(h, lw));
+  ZETT_CUDA(cudaDeviceSynchronize());
+  ZETT_CUDA(cudaMemset(h->flags, 0, sizeof(unsigned int) * kFlagSlots));
   return ZETT_OK;
 }
 
@@ -1231,40 +1265,76 @@ void zett_hn_destroy(zett_hn* h) {
   if (!h) return;
   cudaSetDevice(h->gemm.dev.device);
   cudaDeviceSynchronize();
-  for (cudaEvent_t e : h->gemm.events) cudaEventDestroy(e);
   free_workspace(h);
   for (auto& kv : h->staged) cudaFree(kv.second.dev);
+  for (LinearW* lw : h->linears()) if (lw->op) cudaFree(lw->op);
   for (void* p : h->owned) cudaFree(p);
+  if (h->flags) cudaFree(h->flags);
   delete h;
 }
 
-int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev, float* out_dev, int64_t m, int64_t n,
-                  int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms, void* cuda_stream) {
-  if (!a_dev || !w_dev || !out_dev || m <= 0 || n <= 0 || k <= 0) return fail(ZETT_ERR_INVALID, "bad argument");
-  if ((m * k) % 4 || (n * k) % 4 || k % 8 || n % 8) return fail(ZETT_ERR_INVALID, "sizes must be multiples of 8");
+// decode the fp32 value an ACTIVATION operand line stands for (main plane + first-order correction): the unit tests compare
+// the operand-line output of a GEMM with its fp32 output
+__global__ void decode_operand_kernel(const uint8_t* base, long long ld_bytes, int fmt, long long rows, int k, float* out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * k;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / k;
+    const int c = static_cast<int>(i % k);
+    float v = operand_plane(base, ld_bytes, fmt, r, c, 0);
+    if (fmt == kFmtF16F8) v += operand_plane(base, ld_bytes, fmt, r, c, 1) * kF8Down;   // q0 = 2^6 (x - p0)
+    else if (fmt == kFmtBf16x3) v += operand_plane(base, ld_bytes, fmt, r, c, 1);
+    out[i] = v;
+  }
+}
+
+int zett_gemm_f32_ex(const float* a_dev, const float* w_dev, const float* bias_dev, const float* residual_dev,
+                     const float* col_scale_dev, const float* col_shift_dev, float* out_dev, float* out_operand_dev, int64_t m,
+                     int64_t n, int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms, char* report,
+                     int64_t report_cap, void* cuda_stream) {
+  if (!a_dev || !w_dev || m <= 0 || n <= 0 || k <= 0) return fail(ZETT_ERR_INVALID, "bad argument");
+  if (k % 8 || n % 8) return fail(ZETT_ERR_INVALID, "N and K must be multiples of 8");
+  if (report && report_cap > 0) report[0] = 0;
   GemmEngine eng;
   ZETT_TRY(query_device(&eng.dev));
   ZETT_TRY(set_kernel_attrs(&eng.dev));
   eng.impl = impl == 0 ? 5 : impl;
-  eng.set_precision(split_terms);
+  if (eng.impl != 2 && eng.impl != 3 && eng.impl != 5) return fail(ZETT_ERR_INVALID, "impl must be 0, 2, 3 or 5");
+  eng.set_precision(split_terms == 0 ? 2 : split_terms);
   eng.read_env();
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-  uint16_t *pa = nullptr, *pw = nullptr;
-  ZETT_CUDA(cudaMalloc(&pa, sizeof(uint16_t) * 2 * m * k));
-  ZETT_CUDA(cudaMalloc(&pw, sizeof(uint16_t) * 2 * n * k));
-  auto cleanup = [&]() { cudaFree(pa); cudaFree(pw); };
-  const int two = eng.n_terms != 1;
-  split_planes_kernel<<<1184, 256, 0, stream>>>(a_dev, m * k / 4, pa, two ? pa + m * k : nullptr, 0, eng.split_fmt, false);
-  split_planes_kernel<<<1184, 256, 0, stream>>>(w_dev, n * k / 4, pw, two ? pw + n * k : nullptr, 0, eng.split_fmt, true);
+  const int fmt = eng.fmt;
+  const long long ld = operand_ld_bytes(fmt, k), ld_n = operand_ld_bytes(fmt, n);
+  uint8_t *pa = nullptr, *pw = nullptr, *po = nullptr;
+  float* inv_scale = nullptr;
+  unsigned int* sat = nullptr;
+  auto cleanup = [&]() { cudaFree(pa); cudaFree(pw); cudaFree(po); cudaFree(inv_scale); cudaFree(sat); };
+  ZETT_CUDA(cudaMalloc(&pa, static_cast<size_t>(m * ld)));
+  ZETT_CUDA(cudaMalloc(&pw, static_cast<size_t>(n * ld)));
+  ZETT_CUDA(cudaMalloc(&inv_scale, sizeof(float) * n));
+  ZETT_CUDA(cudaMalloc(&sat, sizeof(unsigned int)));
+  ZETT_CUDA(cudaMemsetAsync(pa, 0, static_cast<size_t>(m * ld), stream));
+  ZETT_CUDA(cudaMemsetAsync(pw, 0, static_cast<size_t>(n * ld), stream));
+  ZETT_CUDA(cudaMemsetAsync(sat, 0, sizeof(unsigned int), stream));
+  if (out_operand_dev) {
+    ZETT_CUDA(cudaMalloc(&po, static_cast<size_t>(m * ld_n)));
+    ZETT_CUDA(cudaMemsetAsync(po, 0, static_cast<size_t>(m * ld_n), stream));
+  }
+  const bool scaled = fmt == kFmtF16F8;
+  split_rows_kernel<<<static_cast<int>(std::min<int64_t>(m, 148 * 16)), 256, 0, stream>>>(a_dev, m, static_cast<int>(k),
+                                                                                         OperandOut{pa, ld, fmt, sat}, 0, false, nullptr);
+  split_rows_kernel<<<static_cast<int>(std::min<int64_t>(n, 148 * 16)), 256, 0, stream>>>(w_dev, n, static_cast<int>(k),
+                                                                                         OperandOut{pw, ld, fmt, sat}, 0, true,
+                                                                                         scaled ? inv_scale : nullptr);
   GemmArgs g;
-  g.a = pa; g.a_rows = m; g.a_plane_stride = m * k;
-  g.w = pw; g.w_plane_stride = n * k;
-  g.a_q = reinterpret_cast<const uint8_t*>(pa + m * k);
-  g.w_q = reinterpret_cast<const uint8_t*>(pw + n * k);
+  g.a = pa; g.a_rows = m; g.a_ld = ld;
+  g.w = pw; g.w_ld = ld;
   g.n = static_cast<int>(n); g.k = static_cast<int>(k); g.m_host = static_cast<int>(m);
   // act bit 8 = timing probe: run the full main loop and epilogue arithmetic but store nothing
-  g.ep.bias = bias_dev; g.ep.act = act & 0xFF; g.ep.out_f32 = (act & 0x100) ? nullptr : out_dev; g.ep.ld_out = n;
-  g.ep.split_fmt = eng.split_fmt;
+  g.ep.bias = bias_dev; g.ep.w_scale = scaled ? inv_scale : nullptr; g.ep.act = act & 0xFF;
+  g.ep.residual = residual_dev; g.ep.ld_res = n;
+  g.ep.col_scale = col_scale_dev; g.ep.col_shift = col_shift_dev;
+  g.ep.out_f32 = (act & 0x100) ? nullptr : out_dev; g.ep.ld_out = n;
+  g.ep.out_op = po ? OperandOut{po, ld_n, fmt, sat} : OperandOut{nullptr, 0, 0, nullptr};
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   int rc = eng.launch(g, stream);  // warm-up / the result
@@ -1273,14 +1343,28 @@ int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev,
     for (int i = 0; i < std::max(iters, 1) && rc == ZETT_OK; ++i) rc = eng.launch(g, stream);
     cudaEventRecord(e1, stream);
   }
+  if (rc == ZETT_OK && po) {
+    decode_operand_kernel<<<1184, 256, 0, stream>>>(po, ld_n, fmt, m, static_cast<int>(n), out_operand_dev);
+  }
   cudaError_t e = cudaStreamSynchronize(stream);
   if (rc == ZETT_OK && e != cudaSuccess) {
     rc = fail(ZETT_ERR_CUDA, std::string("GEMM kernel fault: ") + cudaGetErrorString(e) + watchdog_text());
   }
   if (rc == ZETT_OK && elapsed_ms) cudaEventElapsedTime(elapsed_ms, e0, e1);
+  if (rc == ZETT_OK && report && report_cap > 0) {
+    const std::string r = eng.prof_report();
+    snprintf(report, static_cast<size_t>(report_cap), "%s", r.c_str());
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cleanup();
   return rc;
+}
+
+int zett_gemm_f32(const float* a_dev, const float* w_dev, const float* bias_dev, float* out_dev, int64_t m, int64_t n,
+                  int64_t k, int act, int impl, int split_terms, int iters, float* elapsed_ms, void* cuda_stream) {
+  if (!out_dev) return fail(ZETT_ERR_INVALID, "bad argument");
+  return zett_gemm_f32_ex(a_dev, w_dev, bias_dev, nullptr, nullptr, nullptr, out_dev, nullptr, m, n, k, act, impl, split_terms, iters,
+                          elapsed_ms, nullptr, 0, cuda_stream);
 }
 
 }  // extern "C"

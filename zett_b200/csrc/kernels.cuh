@@ -5,7 +5,7 @@
 //   gather_rescale_kernel   ids -> source / fallback embedding rows, in_scaler, 16-bit split (modeling_hypernet.py:179-188)
 //   layernorm_kernel        (x [+ residual] [+ type/position embeddings]) -> LayerNorm -> fp32 + split planes
 //   attention_kernel        per (row, heads of one warp) softmax(q k^T / sqrt(dh) + mask) v over <= S packed positions
-//   split_planes_kernel     fp32 -> operand planes of the GEMM engine (weights at load time)
+//   split_rows_kernel       fp32 -> operand lines of the GEMM engine (weights at load time, with their per-row scales)
 //   gemm_simt_kernel        same contract as gemm_tcgen05_kernel, CUDA cores, for checking
 //
 // Packing.  A surface-form row holds L ids, most of them pad (mean non-pad length ~2.9 of 7 on the benchmark
@@ -35,6 +35,7 @@ struct PackParams {
   int pad_id, v0, n_fallback;  // n_fallback = max(hn_n_extra_tokens, 1)
   int lang_slot;               // 1 when a lang-id position is appended to every row
   int* counts;                 // [kCntSlots], zeroed before the pass
+  unsigned int* sticky_bad;    // handle-wide flag, set when any id of any pass was out of range (cleared by zett_hn_check)
   int* row_cnt;                // [n_rows]      kept positions of each row
   int* row_start1;             // [n_rows + 1]  surface packing (input projection)
   int* row_start2;             // [n_rows + 1]  encoder packing (surface positions + lang slot)
@@ -83,7 +84,10 @@ __global__ void __launch_bounds__(kPackBlock) pack_count_kernel(const PackParams
   p.row_cnt[r] = __popc(kept_mask(row, p.L, p.pad_id, p.lang_slot, nonpad));
   int bad = 0;
   for (int q = 0; q < p.L; ++q) bad |= (row[q] < 0 || row[q] >= id_limit) ? 1 : 0;
-  if (bad) atomicOr(&p.counts[kCntBadId], 1);
+  if (bad) {
+    atomicOr(&p.counts[kCntBadId], 1);
+    atomicOr(p.sticky_bad, 1u);
+  }
 }
 
 // (2) one block: exclusive scan of the per-row counts -> row starts of both packings, totals
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(kPackBlock) pack_index_kernel(const PackParams
 // Gather + rescale + split.  One CTA streams whole embedding rows: each row is fetched with ONE bulk async copy
 // (cp.async.bulk, the TMA engine's linear mode) into a double-buffered shared-memory stage, so the HBM reads are
 // full-line and independent of the thread mapping; the threads then apply  w * x + b  (in_scaler, not for fallback
-// rows), split into the two 16-bit planes the input-projection GEMM consumes and store 16 bytes per plane per thread.
+// rows) and write the operand lines the input-projection GEMM consumes (operand.cuh).
 // Algorithmic bytes per position: 4 E read + 4 E written.
 // -------------------------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
@@ -209,9 +213,7 @@ struct GatherParams {
   const int* tok_src;
   const int* n_tok;        // device count
   int E;
-  int split_fmt;
-  uint16_t* out_p0;        // [cap, E]
-  uint16_t* out_p1;        // nullable (single-plane mode)
+  OperandOut out;          // [cap, E] operand lines
 };
 
 __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const GatherParams p) {
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const Ga
     bulk_load_1d(smem_u32(stage[0]), row_ptr(t), row_bytes, bar[0]);
   }
   uint32_t phase[2] = {0u, 0u};
+  uint32_t bad = 0;
   int buf = 0;
   for (; t < n_tok; t += gridDim.x, buf ^= 1) {
     const int t_next = t + gridDim.x;
@@ -252,10 +255,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const Ga
     phase[buf] ^= 1u;
     const bool rescale = p.scale_w != nullptr && __ldg(p.tok_src + t) >= 0;
     const float* x = stage[buf];
-    uint16_t* o0 = p.out_p0;
-    uint16_t* o1 = p.out_p1;
-    for (long long e0 = tid * 8; e0 < p.E; e0 += kGatherThreads * 8) {
-      const long long e = static_cast<long long>(t) * p.E + e0;
+    for (int e0 = tid * 8; e0 < p.E; e0 += kGatherThreads * 8) {
       float v[8];
       *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(x + e0);
       *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(x + e0 + 4);
@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const Ga
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(__fmul_rn(w[i], v[i]), b[i]);  // Rescaler: w * x + b, two roundings
       }
-      store_operand8(o0, o1, e, v, p.split_fmt, false);
+      store_operand8(p.out, t, e0, v, false, bad);
     }
     __syncthreads();  // everyone is done reading stage[buf] before it is refilled two iterations from now
   }
+  report_saturation(p.out.sat, bad);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -304,14 +305,11 @@ struct LnParams {
   int n_host;
   const int* out_index;      // nullable
   float* out_f32;            // nullable [*, H]
-  uint16_t* out_p0;          // nullable [*, H]
-  uint16_t* out_p1;
-  int split_fmt;
+  OperandOut out_op;         // base nullable: [*, H] operand lines
   const int* tok_row;        // nullable: enables the compact copy for positions with row_start[tok_row[t]] == t
   const int* row_start;
   float* c_f32;
-  uint16_t* c_p0;
-  uint16_t* c_p1;
+  OperandOut c_op;           // base nullable
   const float* dot_w;        // nullable [H]
   const float* dot_b;        // [1]
   float* dot_out;            // [n * dot_ld]
@@ -331,10 +329,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__device__ __forceinline__ void store_split4(uint16_t* p0, uint16_t* p1, long long off, const float4 y, int fmt,
-                                             bool is_weight = false) {
+__device__ __forceinline__ void store_split4(const OperandOut& o, long long row, int col, const float4 y, bool is_weight, uint32_t& bad) {
   const float v[4] = {y.x, y.y, y.z, y.w};
-  store_operand4(p0, p1, off, v, fmt, is_weight);
+  store_operand4(o, row, col, v, is_weight, bad);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -355,6 +352,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const int row_threads = WARP ? 32 : blockDim.x;
   const int rows_per_block = WARP ? (blockDim.x >> 5) : 1;
   auto row_sum = [&](float v) { return WARP ? warp_sum(v) : block_sum(v, red); };
+  uint32_t bad = 0;
   for (int t = blockIdx.x * rows_per_block + (WARP ? (threadIdx.x >> 5) : 0); t < n; t += gridDim.x * rows_per_block) {
     float4 v[VEC];
     const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(p.in_index ? __ldg(p.in_index + t) : t) * p.lda);
@@ -391,12 +389,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
     const float var = row_sum(q) / static_cast<float>(p.H);
     const float rstd = 1.0f / sqrtf(var + p.eps);
 
-    const long long o = static_cast<long long>(p.out_index ? __ldg(p.out_index + t) : t) * p.H;
-    long long co = -1;
+    const long long orow = p.out_index ? __ldg(p.out_index + t) : t;
+    const long long o = orow * p.H;
+    long long crow = -1;
     if (p.tok_row) {
       const int r = __ldg(p.tok_row + t);
-      if (__ldg(p.row_start + r) == t) co = static_cast<long long>(r) * p.H;
+      if (__ldg(p.row_start + r) == t) crow = r;
     }
+    const long long co = crow * p.H;
     float dot = 0.f;
     const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
     const float4* b4 = reinterpret_cast<const float4*>(p.beta);
@@ -412,10 +412,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
         y.z = (v[c].z - mean) * rstd * g.z + b.z;
         y.w = (v[c].w - mean) * rstd * g.w + b.w;
         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o + 4 * i) = y;
-        if (p.out_p0) store_split4(p.out_p0, p.out_p1, o + 4 * i, y, p.split_fmt);
-        if (co >= 0) {
+        if (p.out_op.base) store_split4(p.out_op, orow, 4 * i, y, false, bad);
+        if (crow >= 0) {
           if (p.c_f32) *reinterpret_cast<float4*>(p.c_f32 + co + 4 * i) = y;
-          if (p.c_p0) store_split4(p.c_p0, p.c_p1, co + 4 * i, y, p.split_fmt);
+          if (p.c_op.base) store_split4(p.c_op, crow, 4 * i, y, false, bad);
         }
         if (w4) {
           const float4 w = __ldg(w4 + i);
@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       if (lane_in_row == 0) p.dot_out[static_cast<long long>(t) * p.dot_ld] = d + __ldg(p.dot_b);
     }
   }
+  if (p.out_op.base || p.c_op.base) report_saturation(p.out_op.base ? p.out_op.sat : p.c_op.sat, bad);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
@@ -448,10 +449,7 @@ struct AttnParams {
   int n_rows, n_heads, dh;
   float scale;
   int row0_only;
-  uint16_t* out_p0;              // [*, H]
-  uint16_t* out_p1;
-  long long ld_out;
-  int split_fmt;
+  OperandOut out;                // [*, H] operand lines
 };
 
 template <int LPH, int VPL>
@@ -471,6 +469,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   for (int j = 0; j < n; ++j) valid_mask |= (__ldg(p.valid + t0 + j) != 0 ? 1u : 0u) << j;
   const bool any_valid = valid_mask != 0;
   const int n_q = p.row0_only ? 1 : n;
+  uint32_t bad = 0;
   // K and V are streamed per query (L1-resident re-reads); keeping them in registers was measured slower
   for (int i = 0; i < n_q; ++i) {
     const long long qi = p.row0_only ? r : (p.qkv_index ? __ldg(p.qkv_index + t0 + i) : (t0 + i));
@@ -510,61 +509,79 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
       m = m_new;
     }
     const float inv = 1.0f / l;
-    const long long oi = (p.row0_only ? r : (t0 + i)) * p.ld_out + hoff;
+    const long long orow = p.row0_only ? r : (t0 + i);
     if (head_ok) {
 #pragma unroll
       for (int d = 0; d < VPL; ++d) {
         const float y[4] = {acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv};
-        store_operand4(p.out_p0, p.out_p1, oi + 4 * LPH * d, y, p.split_fmt, false);
+        store_operand4(p.out, orow, hoff + 4 * LPH * d, y, false, bad);
       }
     }
   }
+  report_saturation(p.out.sat, bad);
 }
 
-// fp32 [rows, cols] -> 16-bit planes (same layout); rows * cols must be a multiple of 4
-// `off0`: element offset of x[0] inside the operand buffer (stacked weights), so that the plane addressing of every
-// format is derived from the buffer's base pointers
-__global__ void split_planes_kernel(const float* __restrict__ x, long long n4, uint16_t* p0, uint16_t* p1, long long off0,
-                                    int fmt, bool is_weight) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 y = __ldg(reinterpret_cast<const float4*>(x) + i);
-    store_split4(p0, p1, off0 + 4 * i, y, fmt, is_weight);
+// fp32 [rows, k] -> operand lines, one block per row (k a multiple of 4).  Weights of kFmtF16F8 are stored scaled by a
+// power of two per row that brings the row maximum into [16, 32) (operand.cuh); `inv_scale[row]` receives the inverse,
+// which the GEMM epilogue applies to output column `row`.  Values outside fp16's range after that are counted in out.sat.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, long long rows, int k, OperandOut out,
+                                                         long long row_off, bool is_weight, float* inv_scale) {
+  __shared__ float red[32];
+  uint32_t bad = 0;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + r * k);
+    float scale = 1.0f;
+    if (inv_scale) {
+      float m = 0.f;
+      for (int i = threadIdx.x; i < k / 4; i += blockDim.x) {
+        const float4 y = __ldg(x4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(y.x), fabsf(y.y))), fmaxf(fabsf(y.z), fabsf(y.w)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+      __syncthreads();
+      m = 0.f;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+      int e = 0;
+      if (m > 0.f && isfinite(m)) {
+        frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(5 - e) in [16, 32)
+        e = max(-100, min(100, 5 - e));
+        scale = ldexpf(1.0f, e);
+      }
+      if (threadIdx.x == 0) inv_scale[row_off + r] = 1.0f / scale;   // a power of two: exact
+    }
+    for (int i = threadIdx.x; i < k / 4; i += blockDim.x) {
+      float4 y = __ldg(x4 + i);
+      y.x *= scale; y.y *= scale; y.z *= scale; y.w *= scale;
+      store_split4(out, row_off + r, 4 * i, y, is_weight, bad);
+    }
   }
+  report_saturation(out.sat, bad);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// SIMT checker GEMM: identical contract and identical product terms (A0 B0 + A1 B0 + A0 B1, fp32 accumulation) as the
-// tcgen05 kernel, on CUDA cores.  128 x 32 output tile per CTA, one thread per row.  Used by the tests to validate
-// the tensor-core path on the device and selectable (gemm_impl = 3) to bisect a failure; never the default.
+// SIMT checker GEMM: identical contract and identical product terms (fp32 accumulation) as the tcgen05 kernel, on CUDA
+// cores, reading the same operand lines.  128 x 32 output tile per CTA, one thread per row.  Used by the tests to
+// validate the tensor-core path on the device and selectable (gemm_impl = 3) to bisect a failure; never the default.
 // -------------------------------------------------------------------------------------------------------------------
 struct SimtGemmParams {
-  const uint16_t* a0; const uint16_t* a1;  // A planes [M, K] (a1 nullable: single term)
-  const uint16_t* w0; const uint16_t* w1;  // W planes [N, K]
-  const uint8_t* aq;                       // kFmtF16F8: interleaved fp8 planes of A / W (epilogue.cuh: f8_offset)
-  const uint8_t* wq;
+  const uint8_t* a; long long a_ld;   // A operand lines [M, a_ld bytes]
+  const uint8_t* w; long long w_ld;   // W operand lines [N, w_ld bytes]
   int m_host; const int* m_dev;
   int n, k;
-  int split_fmt;
+  int fmt;
 };
 
-// value of plane `pl` (0 = main, 1 / 2 = correction planes) of an operand at element offset `off`
-__device__ __forceinline__ float operand_plane(const uint16_t* p0, const uint16_t* p1, const uint8_t* q, long long off, int pl,
-                                               int fmt) {
-  if (pl == 0) return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(p0[off])) : __half2float(__ushort_as_half(p0[off]));
-  if (fmt == kFmtF16F8) return q ? e5m2_to_float(q[f8_offset(off) + (pl == 2 ? 64 : 0)]) : 0.f;
-  if (!p1) return 0.f;
-  return fmt == kFmtBf16 ? __bfloat162float(__ushort_as_bfloat16(p1[off])) : __half2float(__ushort_as_half(p1[off]));
-}
-
 __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, const EpilogueParams ep) {
-  // term t of the product list is As[t] . Ws[t]:  16-bit split: (a0,w0) (a1,w0) (a0,w1);  f16+fp8: (p0,w0) (q0,wq0) (q1,wq1)
+  // term t of the product list is As[t] . Ws[t]:  bf16x3: (hi,hi) (lo,hi) (hi,lo);  f16+fp8: (p0,p0) (q0,q0) (q1,q1);  bf16x1: (hi,hi)
   __shared__ float As[3][128][17], Ws[3][32][17];
   const int M = s.m_dev ? *s.m_dev : s.m_host;
   const int row0 = blockIdx.y * 128, col0 = blockIdx.x * 32;
   if (row0 >= M) return;
   const int tid = threadIdx.x;
-  const bool f8 = s.split_fmt == kFmtF16F8;
+  const bool f8 = s.fmt == kFmtF16F8;
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
@@ -574,10 +591,9 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, 
       const long long gr = row0 + r;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (gr < M && k0 + c < s.k) {
-        const long long off = gr * s.k + k0 + c;
-        x0 = operand_plane(s.a0, s.a1, s.aq, off, 0, s.split_fmt);
-        x1 = operand_plane(s.a0, s.a1, s.aq, off, 1, s.split_fmt);
-        x2 = f8 ? operand_plane(s.a0, s.a1, s.aq, off, 2, s.split_fmt) : x0;
+        x0 = operand_plane(s.a, s.a_ld, s.fmt, gr, k0 + c, 0);
+        x1 = operand_plane(s.a, s.a_ld, s.fmt, gr, k0 + c, 1);
+        x2 = f8 ? operand_plane(s.a, s.a_ld, s.fmt, gr, k0 + c, 2) : x0;
       }
       As[0][r][c] = x0; As[1][r][c] = x1; As[2][r][c] = x2;
     }
@@ -586,14 +602,13 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, 
       const long long gn = col0 + r;
       float y0 = 0.f, y1 = 0.f, y2 = 0.f;
       if (gn < s.n && k0 + c < s.k) {
-        const long long off = gn * s.k + k0 + c;
-        y0 = operand_plane(s.w0, s.w1, s.wq, off, 0, s.split_fmt);
+        y0 = operand_plane(s.w, s.w_ld, s.fmt, gn, k0 + c, 0);
         if (f8) {
-          y1 = operand_plane(s.w0, s.w1, s.wq, off, 1, s.split_fmt);
-          y2 = operand_plane(s.w0, s.w1, s.wq, off, 2, s.split_fmt);
+          y1 = operand_plane(s.w, s.w_ld, s.fmt, gn, k0 + c, 1);
+          y2 = operand_plane(s.w, s.w_ld, s.fmt, gn, k0 + c, 2);
         } else {
-          y1 = s.a1 ? y0 : 0.f;
-          y2 = operand_plane(s.w0, s.w1, s.wq, off, 1, s.split_fmt);
+          y1 = y0;                                                    // A_lo . W_hi (A_lo is zero in the one-term format)
+          y2 = operand_plane(s.w, s.w_ld, s.fmt, gn, k0 + c, 1);      // A_hi . W_lo
         }
       }
       Ws[0][r][c] = y0; Ws[1][r][c] = y1; Ws[2][r][c] = y2;
@@ -608,7 +623,9 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const SimtGemmParams s, 
     __syncthreads();
   }
   const int row = row0 + tid;
-  if (row < M) epilogue_store32(ep, row, col0, min(32, s.n - col0), acc);
+  uint32_t bad = 0;
+  if (row < M) epilogue_row32(ep, row, col0, s.n, acc, bad);
+  report_saturation(ep.out_op.sat, bad);
 }
 
 }  // namespace zett

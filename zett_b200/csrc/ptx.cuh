@@ -34,6 +34,24 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Warp index as a value the compiler knows to be warp-uniform (a shuffle from lane 0), so that role dispatch is a uniform
+// branch and everything computed inside it from uniform inputs stays on the uniform datapath: tcgen05.mma / TMA / commit
+// take their operands from uniform registers, and a divergent `if (lane == 0)` around them makes ptxas wrap EVERY issue
+// in an elect / R2UR.BROADCAST waterfall loop (~25 instructions and several dependent round trips per MMA).
+__device__ __forceinline__ int warp_index_uniform() {
+  return __shfl_sync(0xFFFFFFFFu, static_cast<int>(threadIdx.x >> 5), 0);
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -118,6 +136,18 @@ __device__ __forceinline__ void tma_load_3d_2sm_mc(const void* tmap, uint32_t ba
       " [%0], [%1, {%4, %5, %6}], [%2], %3, %7;"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
       : "memory");
+}
+// 2-D tiled loads of operand lines (rows of 128-byte lines, uint8 tensor maps): {byte column, row}
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+// CTA-pair variant: data lands in this CTA's smem, bytes are credited to the mbarrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy) : "memory");
 }
 // 1-D bulk copy global -> smem (gather of whole embedding rows)
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

@@ -69,6 +69,7 @@ class NativeHypernet:
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device
+        self.auto_terms = int(split_terms) == 0   # the caller left the operand format to the library: fallback allowed
         self.handle = ctypes.c_void_p()
         with torch.cuda.device(device):
             _lib.check(self.lib.zett_hn_create(ctypes.byref(make_c_config(cfg, max_rows_per_pass, gemm_impl, split_terms)),
@@ -118,6 +119,28 @@ class NativeHypernet:
         """Synchronise the current stream and raise what the kernels recorded (IndexError for out-of-range ids)."""
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.zett_hn_check(self.handle, ctypes.c_void_p(stream)))
+
+    def set_split_terms(self, terms: int):
+        """Switch the operand format of the handle (``zett_hn_set_split_terms``); synchronises the device."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.zett_hn_set_split_terms(self.handle, int(terms)))
+
+    def run_checked(self, enqueue, allow_fallback: bool = True):
+        """``enqueue()`` (any number of ``forward_into`` calls) followed by ``check()``.  When the kernels report an operand
+        outside fp16's range (``OperandRangeError``) and the operand format was left on auto, the handle switches to the
+        three-term bf16 split -- fp32's exponent range, the semantics of the fp32 reference
+        (hf_hypernet/modeling_hypernet.py:179-189) -- and the work is enqueued and checked again."""
+        enqueue()
+        try:
+            self.check()
+        except _lib.OperandRangeError as e:
+            if not (self.auto_terms and allow_fallback):
+                raise
+            import warnings
+            warnings.warn("zett_b200: %s -- switching this model to split_terms = 3 (three bf16 terms) and repeating the forward" % e)
+            self.set_split_terms(3)
+            enqueue()
+            self.check()
 
     def stats(self) -> dict:
         st = _lib.ZettHnStats()
@@ -253,9 +276,10 @@ class ZettHypernet(PreTrainedModel):
         pred_out = torch.empty((n, D), dtype=torch.float32, device=device) if self.has_separate_out_embeddings else None
         pred_bias = torch.empty((n,), dtype=torch.float32, device=device)
         if n > 0:
-            nat.forward_into(sf, src, lang, pred_in, pred_out, pred_bias)
             if self.check_ids:
-                nat.check()
+                nat.run_checked(lambda: nat.forward_into(sf, src, lang, pred_in, pred_out, pred_bias))
+            else:
+                nat.forward_into(sf, src, lang, pred_in, pred_out, pred_bias)
         if squeeze:
             return pred_in[0], (None if pred_out is None else pred_out[0]), pred_bias[0]
         return pred_in, pred_out, pred_bias

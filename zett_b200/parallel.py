@@ -57,6 +57,9 @@ def predict_sharded(n_rows: int, n_embd: int, separate_out: bool, compute_block:
     if hi > lo:
         compute_block(lo, hi, block)
     full = gather_rows(block, world, group)
+    check = getattr(compute_block, "check", None)
+    if check is not None:
+        check()  # IndexError for an out-of-range id, as ZettHypernet.forward raises (the kernels clamp and only flag it)
     return unpack(full, n_rows, n_embd, separate_out)
 
 
@@ -74,4 +77,5 @@ def hypernet_block_fn(hypernet, surface_forms_dev: torch.Tensor, source_embeddin
         nat.forward_into(sf, source_embeddings_dev, lang, block[:, 0:], block[:, d:] if separate else None,
                          block[:, (2 if separate else 1) * d:], ld_pred=w, ld_bias=w)
 
+    compute.check = nat.check
     return compute

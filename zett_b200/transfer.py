@@ -244,7 +244,20 @@ class TokenPipeline:
     def run(self, tokens, after_compute=None):
         """Returns ``(out_pinned[:n] as [n, n_out * D + 4] fp32, surface_forms [n, L] int32, n_truncated)``; columns
         are ``pred_in | pred_out | bias`` (``zett_b200.parallel.unpack`` splits them).  ``after_compute(block)`` runs on
-        the compute stream after the last pass (the all-gather of the multi-GPU path)."""
+        the compute stream after the last pass (the all-gather of the multi-GPU path).  Like ``ZettHypernet.forward`` the
+        call raises ``IndexError`` for an out-of-range id in ANY pass (the library's flag is sticky across passes) and
+        repeats itself with the bf16 operand split when a value left fp16's range (single-process use only: a collective
+        in ``after_compute`` must not be repeated by one rank alone)."""
+        result = {}
+
+        def enqueue():
+            result["v"] = self._run_once(tokens, after_compute)
+
+        self.nat.run_checked(enqueue, allow_fallback=after_compute is None)
+        self.copy_stream.synchronize()
+        return result["v"]
+
+    def _run_once(self, tokens, after_compute=None):
         from .parallel import packed_width
         cfg = self.cfg
         n, D, separate = len(tokens), cfg.n_embd, bool(cfg.separate_out_embeddings)
@@ -271,8 +284,6 @@ class TokenPipeline:
             events.append(ev)
         if after_compute is not None:
             after_compute(self.block[:n])
-        self.copy_stream.synchronize()
-        stream.synchronize()
         return self.out_pinned[:n], self.sf_pinned[:n].numpy(), n_trunc
 
 
