@@ -96,7 +96,7 @@ class ClockSampler:
 
 
 def build_workload(name, rank, rows):
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     wl = WORKLOADS[name]
     cfg = synthetic.make_config(name)
     hn = synthetic.make_hn_tokenizer(wl["hn"], 32000, seed=1, pad_token="</s>" if cfg.pad_token_id == 2 else "<pad>",
@@ -113,7 +113,7 @@ def cpu_reference_run(name, steps, warmup, budget_s):
     import torch
     from oracle import hypernet_oracle_torch as hot
     from oracle import retok_oracle as ro
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wl = WORKLOADS[name]
@@ -151,7 +151,7 @@ def torch_eager_gpu_run(name, dev, rows=8192):
     sm_100 kernels) on the same B200, fp32 and with TF32 matmuls enabled.  Rows are independent, so a sample is timed."""
     import torch
     from oracle import hypernet_oracle_torch as hot
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     wl = WORKLOADS[name]
     cfg = synthetic.make_config(name)
     W = hot.to_torch(synthetic.make_weights(cfg, seed=0), dev)
@@ -229,7 +229,8 @@ def profile_of_largest_gemm(config, fmt_tag, impl):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from zett_b200 import parallel, synthetic
+    import zett_synthetic as synthetic
+from zett_b200 import parallel
     from zett_b200.modeling_hypernet import NativeHypernet
     from zett_b200.surface_forms import get_surface_form_matrix
 

@@ -170,6 +170,36 @@ int zett_gemm_f32_ex(const float* a_dev, const float* w_dev, const float* bias_d
                      char* report, int64_t report_cap, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, row blocks of the vocabulary per rank, the predicted rows of all ranks assembled on
+ * every rank by ncclAllGather (NVLink / NVSwitch).
+ * Replaces the reference's sharding of an inference batch over the local devices
+ *      SHARDING = PositionalSharding(jax.local_devices())                 (reference zett/utils.py:26)
+ *      jax.device_put(batch, SHARDING.reshape((-1, 1))) ... device_get    (reference scripts/transfer.py:90-91, 105-111)
+ * with replicated hypernet parameters and source-embedding table.  NCCL is bound at run time (dlopen libnccl.so.2,
+ * preferring the copy already in the process), so single-GPU callers never need it.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct zett_comm zett_comm;
+
+/* Rank 0 fills 128 bytes (ncclUniqueId) and hands them to the other ranks by whatever means the host application has
+ * (MPI, a file, torch.distributed.broadcast_object_list ...). */
+int zett_comm_unique_id(void* out_id_128_bytes);
+
+/* Collective over all `world` ranks, each on its own process with its CUDA device current.  world == 1 needs no id
+ * (and no NCCL). */
+int zett_comm_init(int rank, int world, const void* nccl_unique_id, zett_comm** out);
+
+/* full_dev[world * rows_per_rank, row_elems] <- concatenation over ranks of shard_dev[rows_per_rank, row_elems]
+ * (fp32, device pointers, row-major, every rank the same sizes), enqueued on `cuda_stream`; no synchronisation.
+ * shard_dev may alias this rank's slot of full_dev (in-place all-gather).  world == 1: shard_dev must be full_dev. */
+int zett_allgather_rows(zett_comm* c, const float* shard_dev, int64_t rows_per_rank, int64_t row_elems, float* full_dev,
+                        void* cuda_stream);
+
+/* rank / world of the communicator and the NCCL version in use (0 when world == 1); any pointer may be NULL */
+int zett_comm_info(const zett_comm* c, int* rank, int* world, int* nccl_version);
+
+void zett_comm_destroy(zett_comm* c);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Surface forms.
  * Replaces get_surface_form_matrix                  (reference zett/utils.py:651-689)
  * and the tokenizers.models.{Unigram,BPE}.tokenize call it makes per token (zett/utils.py:681; third-party Rust).

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import hypernet_oracle as ho  # noqa: E402
 from oracle import hypernet_oracle_torch as hot  # noqa: E402
-from zett_b200 import synthetic  # noqa: E402
+import zett_synthetic as synthetic  # noqa: E402
 
 
 def r16(x, dt):

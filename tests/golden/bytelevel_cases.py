@@ -35,7 +35,7 @@ def unigram_metaspace(byte_fallback=True):
 
 def bpe_bytelevel():
     """GPT-2-style byte-level BPE with an <|endoftext|> special and an added whitespace token."""
-    from zett_b200.synthetic import BYTES_TO_CHARS
+    from zett_b200.byte_alphabet import BYTES_TO_CHARS
     alphabet = [BYTES_TO_CHARS[b] for b in range(256)]
     vocab = {c: i for i, c in enumerate(alphabet)}
     merges = []

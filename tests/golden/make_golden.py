@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 REFERENCE = "/root/reference"
 
-from zett_b200 import synthetic  # noqa: E402
+import zett_synthetic as synthetic  # noqa: E402
 
 
 def load_reference_hypernet():

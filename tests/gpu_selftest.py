@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import hypernet_oracle as ho  # noqa: E402
-from zett_b200 import _lib, synthetic  # noqa: E402
+import zett_synthetic as synthetic
+from zett_b200 import _lib  # noqa: E402
 from zett_b200.modeling_hypernet import NativeHypernet  # noqa: E402
 
 GEMM_CASES = [
@@ -151,22 +152,22 @@ def run_gemm(impl: int):
     return ok
 
 
-def run_sweep():
+def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2)):
     """Timing probes of the GEMM engine (no parity claim): ms per launch over shapes x formats x tile shapes, with the
     per-role stall picture of one launch when ZETT_GEMM_PROF=1."""
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    shapes = [(16384, 4096, 4096), (53248, 12288, 4096), (53248, 4096, 8192), (53248, 8192, 4096), (54000, 2304, 768),
-              (54000, 1536, 768), (54000, 768, 1536), (53248, 6144, 2048), (53248, 4096, 2048)]
+    shapes = shapes or [(16384, 4096, 4096), (53248, 12288, 4096), (53248, 4096, 8192), (53248, 8192, 4096), (54000, 2304, 768),
+                        (54000, 1536, 768), (54000, 768, 1536), (53248, 6144, 2048), (53248, 4096, 2048)]
     for (m, n, k) in shapes:
         a = torch.randn(m, k, device=dev)
         w = torch.randn(n, k, device=dev) / k ** 0.5
         b = torch.randn(n, device=dev) * 0.1
         out = torch.empty((m, n), device=dev)
-        for impl in (2, 5):
-            for terms in (2, 3, 1):
-                for act in (0, 0x100, 2):
+        for impl in impls:
+            for terms in terms_list:
+                for act in acts:
                     iters = 4
                     ms, rep = _gemm_ex(lib, a, w, b, None, None, None, out, None, act, impl, terms, iters=iters, report=True)
                     t = ms / iters
@@ -361,12 +362,14 @@ def main():
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--configs", default="tiny,tiny_lang,tiny_single_head,tiny_plain,tiny_one_layer,tiny_multi_pass")
     ap.add_argument("--terms", type=int, default=0)
+    ap.add_argument("--sweep-terms", default="2,3,1")
     args = ap.parse_args()
     if args.what == "one":
         m, n, k = [int(x) for x in args.mnk.split(",")]
         ok = run_one(m, n, k, args.impl or 5, args.terms or 2)
     elif args.what == "sweep":
-        ok = run_sweep()
+        shapes = None if args.mnk == "16384,4096,4096" else [tuple(int(x) for x in t.split(",")) for t in args.mnk.split(";")]
+        ok = run_sweep(shapes, terms_list=tuple(int(x) for x in args.sweep_terms.split(",")))
     elif args.what == "sustained":
         ok = run_sustained([tuple(int(x) for x in t.split(",")) for t in args.mnk.split(";")])
     elif args.what == "gemm":

@@ -1,5 +1,7 @@
-"""Multi-GPU parity check (run under torchrun on N GPUs of one box): the row-sharded prediction assembled by the single
-NCCL all-gather equals the single-GPU prediction bit for bit, on every rank, and matches the oracle on a sample."""
+"""Multi-GPU parity check (run under torchrun on N GPUs of one box; tests/test_multi_gpu.py launches it): the row-sharded
+prediction assembled by the library's own all-gather (zett_comm_init / zett_allgather_rows = ncclAllGather, one per
+super-block, on a side stream) equals the single-GPU prediction bit for bit, on every rank, and matches the oracle on a
+sample."""
 import os
 import sys
 
@@ -11,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import hypernet_oracle as ho  # noqa: E402
-from zett_b200 import parallel, synthetic  # noqa: E402
+import zett_synthetic as synthetic
+from zett_b200 import parallel  # noqa: E402
 from zett_b200.modeling_hypernet import ZettHypernet, load_weights_numpy  # noqa: E402
 
 
@@ -20,6 +23,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    comm = parallel.NativeComm.from_torch_distributed()
+    info = comm.info()
+    assert info["world"] == world and info["rank"] == rank and (world == 1 or info["nccl_version"] > 0), info
     ok = True
     for name, rows, lang in (("tiny", 1003, None), ("xlmr", 4099, 3)):
         cfg = synthetic.make_config(name)
@@ -30,8 +36,14 @@ def main():
         sf, src = torch.from_numpy(sf_np).to(dev), torch.from_numpy(src_np).to(dev)
         single = model(sf, source_embeddings=src, lang_index=None if lang is None else torch.tensor(lang))
         fn = parallel.hypernet_block_fn(model, sf, src, lang)
-        sharded = parallel.predict_sharded(rows, cfg.n_embd, bool(cfg.separate_out_embeddings), fn, dev)
-        torch.cuda.synchronize()
+        for rpp in (None, 96):
+            sharded = parallel.predict_sharded(rows, cfg.n_embd, bool(cfg.separate_out_embeddings), fn, dev, comm=comm,
+                                               rows_per_pass=rpp)
+            torch.cuda.synchronize()
+            for a, b in zip(single, sharded):
+                if a is not None and not torch.equal(a, b.contiguous()):
+                    ok = False
+                    print(f"rank {rank} {name} rows_per_pass {rpp}: sharded != single, max diff {(a - b).abs().max().item():.3e}", flush=True)
         for a, b in zip(single, sharded):
             if a is None:
                 assert b is None
@@ -52,7 +64,8 @@ def main():
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if t.item() == 1 else "FAIL", "world", world, flush=True)
+        print("MULTI_GPU_CHECK", "PASS" if t.item() == 1 else "FAIL", "world", world, "nccl", info["nccl_version"], flush=True)
+    comm.close()
     dist.destroy_process_group()
     sys.exit(0 if t.item() == 1 else 1)
 

@@ -51,7 +51,7 @@ def test_struct_layout_matches_c():
 
 
 def test_unsupported_config_is_rejected_before_any_device_work():
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.modeling_hypernet import make_c_config
     lib = _lib.load()
     h = ctypes.c_void_p()
@@ -72,7 +72,7 @@ def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.modeling_hypernet import ZettHypernet, make_c_config
     lib = _lib.load()
     h = ctypes.c_void_p()

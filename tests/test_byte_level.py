@@ -52,7 +52,7 @@ def test_surface_forms_from_converted_tokenizer():
     """End of the host pipeline: converted target tokenizer -> get_surface_form_matrix (scripts/transfer.py:198-206)."""
     import numpy as np
     from oracle import retok_oracle as ro
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.surface_forms import get_surface_form_matrix
     hn = synthetic.make_hn_tokenizer("unigram", 1200, seed=3)
     target, _ = convert_to_byte_level(bytelevel_cases.bpe_metaspace())

@@ -6,7 +6,7 @@ import os
 import msgpack
 import numpy as np
 
-from zett_b200 import synthetic
+import zett_synthetic as synthetic
 from zett_b200.checkpoint import flax_params_to_state_dict, load_flax_hypernet, read_flax_msgpack
 
 

@@ -70,7 +70,7 @@ def torch_cuda():
 
 
 def _model(torch, name, seed=11, **overrides):
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.modeling_hypernet import ZettHypernet, load_weights_numpy
     cfg = synthetic.make_config(name, **overrides)
     weights = synthetic.make_weights(cfg, seed=seed)
@@ -83,7 +83,7 @@ def test_golden_fixtures_through_public_api(torch_cuda, golden_dir):
     import glob
     torch = torch_cuda
     from oracle import hypernet_oracle as ho
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     for path in sorted(glob.glob(os.path.join(golden_dir, "hypernet_*.npz"))):
         g = np.load(path)
         meta = json.loads(str(g["meta"]))
@@ -105,7 +105,7 @@ def test_golden_fixtures_through_public_api(torch_cuda, golden_dir):
 def test_row_independence_and_idempotence(torch_cuda):
     """Permutation / batch-composition invariance and run-to-run determinism, bit-exact."""
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     cfg, weights, model = _model(torch, "tiny")
     src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
     sf = synthetic.make_random_surface_forms(cfg, 500, seed=3)
@@ -126,7 +126,7 @@ def test_row_independence_and_idempotence(torch_cuda):
 
 def test_out_of_range_id_raises(torch_cuda):
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     cfg, weights, model = _model(torch, "tiny")
     src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
     sf = synthetic.make_random_surface_forms(cfg, 16, seed=3)
@@ -140,7 +140,7 @@ def test_out_of_range_id_raises(torch_cuda):
 
 def test_unsupported_branches_raise(torch_cuda):
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.modeling_hypernet import ZettHypernet
     with pytest.raises(NotImplementedError):
         ZettHypernet(synthetic.make_config("tiny", hn_add_inter_token_attention=True))
@@ -157,7 +157,7 @@ def test_end_to_end_tokens_to_embeddings(torch_cuda):
     against the oracle on the same surface forms; batched_inference == one-shot prediction."""
     torch = torch_cuda
     from oracle import hypernet_oracle as ho
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.surface_forms import get_surface_form_matrix
     from zett_b200.transfer import batched_inference, default_args, make_predict
     hn = synthetic.make_hn_tokenizer("unigram", 316, seed=5, pad_token="</s>")  # ids < tiny's V0 + n_extra = 316
@@ -183,7 +183,7 @@ def test_full_vocab_properties_xlmr(torch_cuda):
     """BASELINE config 2 at full size (50 257 rows, XLM-R shape): size-independent properties -- finite outputs,
     duplicate surface-form rows give bit-identical predictions, pass-size invariance on a slice."""
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     cfg, weights, model = _model(torch, "xlmr")
     src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=12)).cuda()
     sf = synthetic.make_random_surface_forms(cfg, 50257, seed=5)
@@ -201,7 +201,7 @@ def test_pipelined_tokens_path_equals_one_shot(torch_cuda):
     """transfer.predict_from_tokens (retokenise / H2D / compute / D2H overlapped per pass) == one-shot prediction,
     bit for bit, including the surface forms it builds on the way."""
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.surface_forms import get_surface_form_matrix
     from zett_b200.transfer import TokenPipeline, make_predict, predict_from_tokens
     hn = synthetic.make_hn_tokenizer("unigram", 316, seed=5, pad_token="</s>")
@@ -235,7 +235,7 @@ def test_shape_variants(torch_cuda):
     128, a vocabulary of one row and an empty one."""
     torch = torch_cuda
     from oracle import hypernet_oracle as ho
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     # n_embd = 72: GEMM K = 144 and N = 72 are not multiples of 32 (padded operand lines, partial accumulator chunks)
     for overrides in (dict(hn_n_layers=2, hn_surface_maxlen=12), dict(hn_num_attention_heads=4), dict(hn_num_attention_heads=1),
                       dict(n_embd=72)):
@@ -263,7 +263,7 @@ def test_full_vocab_properties_mistral(torch_cuda):
     """BASELINE config 4 at full size (50 304 rows, Mistral-7B shape): finite, duplicate rows identical, and a slice
     recomputed alone reproduces the whole-vocabulary result bit for bit (pass-composition invariance)."""
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.modeling_hypernet import NativeHypernet
     cfg = synthetic.make_config("mistral")
     nat = NativeHypernet(cfg, synthetic.make_weights(cfg, seed=0), torch.device("cuda", 0))
@@ -294,7 +294,7 @@ def test_pair_dedup_is_bit_exact(torch_cuda, name, lang, monkeypatch):
     evaluation bit for bit (same arithmetic on the same operands), with and without the lang-id slot, over several
     passes; the statistics report fewer pairs than positions on a vocabulary with repeated pieces."""
     torch = torch_cuda
-    from zett_b200 import synthetic
+    import zett_synthetic as synthetic
     from zett_b200.modeling_hypernet import NativeHypernet
     cfg = synthetic.make_config(name)
     weights = synthetic.make_weights(cfg, seed=11)

@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import hypernet_oracle as ho
-from zett_b200 import parallel, synthetic
+import zett_synthetic as synthetic
+from zett_b200 import parallel
 from zett_b200.transfer import batched_inference, default_args
 
 
@@ -47,6 +48,29 @@ def test_shard_bounds_cover_all_rows():
     assert parallel.packed_width(4096, True) == 8196 and parallel.packed_width(768, False) == 772
 
 
+def test_shard_plan_covers_all_rows_in_order():
+    """Super-blocks of world * rows_per_pass rows: every row belongs to exactly one (rank, block), blocks tile the padded
+    matrix back to back, padding only past the last row."""
+    for n in (0, 1, 7, 1003, 50304, 262144):
+        for world in (1, 2, 3, 8):
+            for rpp in (1, 16, 4096, 16384, 10 ** 9):
+                plan = parallel.shard_plan(n, world, rpp)
+                owner = np.full(n, -1)
+                nxt = 0
+                for base, per in plan:
+                    assert base == nxt and 1 <= per <= rpp
+                    nxt = base + world * per
+                    for r in range(world):
+                        lo = min(n, base + r * per)
+                        hi = min(n, lo + per)
+                        assert (owner[lo:hi] == -1).all()
+                        owner[lo:hi] = r
+                assert (owner >= 0).all()
+                assert parallel.padded_rows(n, world, rpp) == nxt and nxt >= n and nxt - n < max(1, world)
+                if plan:
+                    assert all(per == min(rpp, per) for _, per in plan[:-1])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -55,7 +79,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_rows, ret):
+def _worker(rank, world, port, n_rows, rows_per_pass, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = synthetic.make_config("tiny")
@@ -70,18 +94,27 @@ def _worker(rank, world, port, n_rows, ret):
         block[: hi - lo, D:2 * D] = torch.from_numpy(b)
         block[: hi - lo, 2 * D] = torch.from_numpy(c)
 
-    pin, pout, pbias = parallel.predict_sharded(n_rows, D, True, compute, torch.device("cpu"))
+    calls = []
+
+    def counted(lo, hi, block):
+        calls.append((lo, hi))
+        compute(lo, hi, block)
+
+    pin, pout, pbias = parallel.predict_sharded(n_rows, D, True, counted, torch.device("cpu"), rows_per_pass=rows_per_pass)
+    if rows_per_pass:
+        assert len(calls) >= n_rows // (world * rows_per_pass)
     ret[rank] = (pin.numpy().copy(), pout.numpy().copy(), pbias.numpy().copy())
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_rows", [101, 64])
-def test_row_sharded_two_ranks_gloo(n_rows):
-    """world_size 2 over gloo: the sharded result equals the single-process result bit for bit on both ranks."""
+@pytest.mark.parametrize("n_rows,rows_per_pass", [(101, None), (64, None), (101, 16), (67, 5)])
+def test_row_sharded_two_ranks_gloo(n_rows, rows_per_pass):
+    """world_size 2 over gloo: the sharded result (one super-block, or several with a gather each) equals the
+    single-process result on both ranks, and the ranks agree bit for bit."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), n_rows, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_rows, rows_per_pass, ret), nprocs=world, join=True)
     cfg = synthetic.make_config("tiny")
     want = ho.hypernet_forward(cfg, synthetic.make_weights(cfg, seed=11), synthetic.make_random_surface_forms(cfg, n_rows, seed=21),
                                synthetic.make_source_embeddings(cfg, seed=12))

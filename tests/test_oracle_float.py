@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import hypernet_oracle as ho
-from zett_b200 import synthetic
+import zett_synthetic as synthetic
 
 CASES = sorted(os.path.basename(p)[len("hypernet_"):-4]
                for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "hypernet_*.npz")))

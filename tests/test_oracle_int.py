@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import retok_oracle as ro
-from zett_b200 import synthetic
+import zett_synthetic as synthetic
 
 INT_CASES = ["unigram", "bpe", "bpe_fuse_ignore"]
 

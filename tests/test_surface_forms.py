@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import retok_oracle as ro
-from zett_b200 import synthetic
+import zett_synthetic as synthetic
 from zett_b200.surface_forms import NativeTokenizerModel, get_surface_form_matrix
 
 INT_CASES = ["unigram", "bpe", "bpe_fuse_ignore"]

@@ -16,10 +16,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libzett_b200.so")
-SOURCES = ["hypernet.cu", "retok.cpp"]
+SOURCES = ["hypernet.cu", "retok.cpp", "comm.cpp"]
 HEADERS = ["ptx.cuh", "operand.cuh", "gemm_tcgen05.cuh", "epilogue.cuh", "kernels.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
 ZETT_OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_INDEX, ERR_KEY, ERR_MISSING_UNK, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6, -7, -8
 ABI_VERSION = 2
@@ -96,6 +96,11 @@ SIGNATURES = {
                               c_int, POINTER(c_float), c_void_p]),
     "zett_gemm_f32_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                  c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), c_char_p, c_int64, c_void_p]),
+    "zett_comm_unique_id": (c_int, [c_void_p]),
+    "zett_comm_init": (c_int, [c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "zett_allgather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "zett_comm_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "zett_comm_destroy": (None, [c_void_p]),
     "zett_tok_create_unigram": (c_int, [POINTER(c_char_p), POINTER(c_double), c_int64, c_int64, c_int, POINTER(c_void_p)]),
     "zett_tok_create_bpe": (c_int, [POINTER(c_char_p), c_int64, POINTER(c_int32), c_int64, c_int64, c_char_p, c_char_p,
                                     c_int, c_int, c_int, POINTER(c_void_p)]),

@@ -28,7 +28,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 import numpy as np
 from tokenizers import Tokenizer, decoders, models, pre_tokenizers
 
-from .synthetic import BYTES_TO_CHARS, CHARS_TO_BYTES
+from .byte_alphabet import BYTES_TO_CHARS, CHARS_TO_BYTES
 
 # zett/utils.py:23,29
 NEGATIVE_INF_FILL_VALUE = -100_000

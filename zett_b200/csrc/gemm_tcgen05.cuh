@@ -120,36 +120,29 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
   return r;
 }
 
-// One 32-row x 32-column accumulator chunk: `v` = this thread's row (tcgen05.ld layout); after the transpose lane l holds
-// the quad (row 4 i + l / 8, columns 4 (l % 8) ..) for i = 0..7.
+// One 32-row x 32-column accumulator chunk, second half of its trip: the rows the warp's threads hold (tcgen05.ld layout:
+// one row per thread) have been written to the warp's staging tile; lane l now takes the quads (row 4 i + l / 8, columns
+// 4 (l % 8) ..) for i = 0..7.  The loop is rolled in two halves of four quads: fully unrolled (with both GELUs inlined) the
+// epilogue alone was ~60 KB of SASS per activation, far beyond the instruction cache, and the K = 768 GEMMs of the XLM-R
+// shape ran at the speed of instruction fetch (epilogue busy 90 % of the kernel, the tensor pipe waiting for accumulators).
 template <int ACT>
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col0, int n,
-                                               const float (&v)[32], uint32_t& bad) {
-  const uint32_t wr = stg + static_cast<uint32_t>(lane) * 128u;
-  const uint32_t sw = static_cast<uint32_t>(lane & 7);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((static_cast<uint32_t>(j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  __syncwarp();
+__device__ __forceinline__ void epilogue_quads(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col,
+                                               const QuadConsts& q, uint32_t& bad) {
   const int jj = lane & 7, rsub = lane >> 3;
-  const int col = col0 + 4 * jj;
-  if (col < n) {
-    const QuadConsts q = load_quad_consts(ep, col);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float4 x[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = 4 * i + rsub;
-      const float4 x = ld_shared_v4(stg + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(jj ^ (rr & 7)) << 4));
-      const long long row = row0 + rr;
-      if (row < M) epilogue_quad<ACT>(ep, row, col, x, q, bad);
+    for (int i = 0; i < 4; ++i) {
+      const int rr = 16 * half + 4 * i + rsub;
+      x[i] = ld_shared_v4(stg + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(jj ^ (rr & 7)) << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long row = row0 + 16 * half + 4 * i + rsub;
+      if (row < M) epilogue_quad<ACT>(ep, row, col, x[i], q, bad);
     }
   }
-  __syncwarp();  // the tile is rewritten by the next chunk
-}
-
-__device__ __forceinline__ void epilogue_chunk_dyn(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col0, int n,
-                                                   const float (&v)[32], uint32_t& bad) {
-  if (ep.act == kActGeluTanh) epilogue_chunk<kActGeluTanh>(ep, stg, lane, row0, M, col0, n, v, bad);
-  else if (ep.act == kActGeluErf) epilogue_chunk<kActGeluErf>(ep, stg, lane, row0, M, col0, n, v, bad);
-  else epilogue_chunk<kActNone>(ep, stg, lane, row0, M, col0, n, v, bad);
 }
 
 // tmap_a: box {128 B, 128 rows} over A's lines;  tmap_b: box {128 B, HALVES * block_n / 2 rows} over W's lines
@@ -315,19 +308,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int col_tile = tc.n_blk * tile_n + hf * load_n;
       auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (HALVES - 1)); };
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
-      // two register chunks: the tcgen05.ld of the next chunk is in flight while the current one is processed
-      float va[32], vb[32];
-      if (c_first < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c_first), va);
-      for (int c = c_first; c < s.block_n; c += 2 * c_step) {
-        const int c2 = c + c_step, c3 = c2 + c_step;
+      // one register chunk: its rows go to the staging tile, then the tcgen05.ld of the NEXT chunk is issued into the same
+      // registers and lands while this chunk's quads are processed out of shared memory
+      float v[32];
+      const uint32_t wr = stg + static_cast<uint32_t>(lane) * 128u;
+      const uint32_t sw = static_cast<uint32_t>(lane & 7);
+      if (c_first < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c_first), v);
+#pragma unroll 1
+      for (int c = c_first; c < s.block_n; c += c_step) {
         tmem_ld_wait();
-        if (c2 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c2), vb);
-        if (gcol(c) < s.n) epilogue_chunk_dyn(ep, stg, lane, row0, M, gcol(c), s.n, va, bad);
-        if (c2 < s.block_n) {
-          tmem_ld_wait();
-          if (c3 < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c3), va);
-          if (gcol(c2) < s.n) epilogue_chunk_dyn(ep, stg, lane, row0, M, gcol(c2), s.n, vb, bad);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((static_cast<uint32_t>(j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (c + c_step < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + c_step), v);
+        const int col = gcol(c) + 4 * (lane & 7);
+        const bool col_ok = col < s.n;
+        QuadConsts q;
+        if (col_ok) q = load_quad_consts(ep, col);
+        __syncwarp();
+        if (col_ok) {
+          if (ep.act == kActGeluErf) epilogue_quads<kActGeluErf>(ep, stg, lane, row0, M, col, q, bad);
+          else if (ep.act == kActGeluTanh) epilogue_quads<kActGeluTanh>(ep, stg, lane, row0, M, col, q, bad);
+          else epilogue_quads<kActNone>(ep, stg, lane, row0, M, col, q, bad);
         }
+        __syncwarp();  // the staging tile is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();

@@ -1,4 +1,6 @@
-"""Seeded synthetic workloads: hypernet configs at the BASELINE shapes, random
+"""Benchmark / test infrastructure, NOT part of the product package.
+
+Seeded synthetic workloads: hypernet configs at the BASELINE shapes, random
 weights with the reference's ``state_dict`` names, source-embedding tables, hn tokenizers (Unigram / BPE)
 and byte-level target vocabularies.  No real tokenizer or checkpoint is reachable offline (the reference's
 ``artifacts/tokenizers/*/tokenizer.json`` are Git-LFS pointers), so tests, ``smoke()`` and ``bench.py``
@@ -10,7 +12,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .config import ZettHypernetConfig, weight_shapes
+from zett_b200.config import ZettHypernetConfig, weight_shapes
 
 # --------------------------------------------------------------------------------------------------
 # configs (hyper-parameters from the reference's shipped configs)
@@ -112,23 +114,7 @@ def make_random_surface_forms(cfg: ZettHypernetConfig, n_rows: int, seed: int = 
     return ids
 
 
-# --------------------------------------------------------------------------------------------------
-# byte alphabet (GPT-2 byte <-> unicode table; reference zett/utils.py:351-609)
-# --------------------------------------------------------------------------------------------------
-def _bytes_to_chars() -> Dict[int, str]:
-    keep = list(range(33, 127)) + list(range(161, 173)) + list(range(174, 256))
-    table, n = {}, 0
-    for b in range(256):
-        if b in keep:
-            table[b] = chr(b)
-        else:
-            table[b] = chr(256 + n)
-            n += 1
-    return table
-
-
-BYTES_TO_CHARS: Dict[int, str] = _bytes_to_chars()
-CHARS_TO_BYTES: Dict[str, int] = {c: b for b, c in BYTES_TO_CHARS.items()}
+from zett_b200.byte_alphabet import BYTES_TO_CHARS, CHARS_TO_BYTES  # noqa: E402,F401
 
 SPECIALS = ["<s>", "<pad>", "</s>", "<unk>"]
 
