@@ -95,14 +95,17 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_workload(name, rank, rows):
+def build_workload(name, rank, rows, vocab="random", hn_kind=None):
     import zett_synthetic as synthetic
     wl = WORKLOADS[name]
     cfg = synthetic.make_config(name)
-    hn = synthetic.make_hn_tokenizer(wl["hn"], 32000, seed=1, pad_token="</s>" if cfg.pad_token_id == 2 else "<pad>",
+    hn = synthetic.make_hn_tokenizer(hn_kind or wl["hn"], 32000, seed=1, pad_token="</s>" if cfg.pad_token_id == 2 else "<pad>",
                                      fit_total=True)
     assert hn.pad_token_id == cfg.pad_token_id, (hn.pad_token_id, cfg.pad_token_id)
-    tokens = synthetic.make_target_tokens(rows, seed=2 + rank)
+    if vocab == "concat":
+        tokens = synthetic.make_concat_tokens(rows, hn, seed=3 + rank)
+    else:
+        tokens = synthetic.make_target_tokens(rows, seed=2 + rank)
     return cfg, hn, tokens
 
 
@@ -110,21 +113,44 @@ def build_workload(name, rank, rows):
 # reference arm / CPU baseline: the reference's CPU execution of the path on host cores, bounded sample
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(name, steps, warmup, budget_s):
+    """The reference's own modules (hf_hypernet.ZettHypernet, zett.utils.get_surface_form_matrix) staged under
+    oracle/_ref by oracle/make_ref.py when they are there (kind "reference"), else the restatement in oracle/ (kind
+    "port"): fp32, all host cores, on a bounded sample of the workload."""
     import torch
     from oracle import hypernet_oracle_torch as hot
+    from oracle import ref_loader
     from oracle import retok_oracle as ro
     import zett_synthetic as synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wl = WORKLOADS[name]
     cfg, hn, tokens = build_workload(name, 0, wl["rows"])
-    W = hot.to_torch(synthetic.make_weights(cfg, seed=0))
+    weights = synthetic.make_weights(cfg, seed=0)
     src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=100))
+    kind = "port"
+    if ref_loader.available():
+        try:
+            model = ref_loader.build_hypernet(cfg, weights)
+            ref_utils = ref_loader.load_utils()
+            kind = "reference"
+        except Exception as e:  # noqa: BLE001
+            print("bench: oracle/_ref not usable (%s); timing the port" % str(e)[:200], file=sys.stderr)
+    if kind == "reference":
+        lang = None if wl["lang"] is None else torch.tensor(wl["lang"])
 
-    def one(sample_tokens):
-        sf, _ = ro.surface_form_matrix_hf(sample_tokens, cfg.hn_surface_maxlen, hn)
-        out = hot.hypernet_forward(cfg, W, sf, src, lang_index=wl["lang"])
-        return out
+        def one(sample_tokens):
+            sf, _ = ref_utils.get_surface_form_matrix(sample_tokens, cfg.hn_surface_maxlen, hn)
+            with torch.no_grad():
+                return model(torch.from_numpy(sf), source_embeddings=src, lang_index=lang)
+        what = "the reference's own get_surface_form_matrix + hf_hypernet.ZettHypernet (oracle/_ref), fp32, eager attention"
+    else:
+        W = hot.to_torch(weights)
+
+        def one(sample_tokens):
+            sf, _ = ro.surface_form_matrix_hf(sample_tokens, cfg.hn_surface_maxlen, hn)
+            return hot.hypernet_forward(cfg, W, sf, src, lang_index=wl["lang"])
+        what = "HF tokenizers loop + threaded ATen fp32 forward (restatement in oracle/)"
+    del weights
 
     # calibrate the sample so that (steps + warmup) samples fit the budget
     n0 = 64
@@ -141,9 +167,8 @@ def cpu_reference_run(name, steps, warmup, budget_s):
     for _ in range(steps):
         t0 = time.perf_counter(); one(sample); times.append(time.perf_counter() - t0)
     mean = float(np.mean(times))
-    return dict(value=n / mean, ms_per_step=mean * 1e3, cores=cores, rows=n,
-                sample="%d of %d rows per step (rows are independent; rows/s extrapolates linearly); HF tokenizers loop + "
-                       "threaded ATen fp32 forward" % (n, wl["rows"]))
+    return dict(value=n / mean, ms_per_step=mean * 1e3, cores=cores, rows=n, kind=kind,
+                sample="%d of %d rows per step (rows are independent; rows/s extrapolates linearly); %s" % (n, wl["rows"], what))
 
 
 def torch_eager_gpu_run(name, dev, rows=8192):
@@ -190,19 +215,24 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["workload"], "rows_per_step": r["rows"], "device": "host CPU"},
-        "cpu_baseline": {"value": r["value"], "unit": "rows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "rows/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def profile_of_largest_gemm(config, fmt_tag, impl):
-    """DRAM bytes (read + write) of one launch of the largest GEMM of the step, from the committed ncu summary."""
+PROFILE_ROUND = "r2"
+
+
+def profile_of_largest_gemm(config, fmt_tag, wide):
+    """DRAM bytes (read + write) of one launch of the largest GEMM of the step, from THIS round's committed ncu summary
+    (profiles/gemm_tcgen05_r2_*.csv; a capture of another round describes another kernel and is refused)."""
     if config != "mistral":
         return None
-    tags = ([fmt_tag + "_wide"] if impl == 5 else []) + [fmt_tag]  # 256 x 512 pair tiles have their own capture
-    for path in [os.path.join(ROOT, "profiles", "gemm_tcgen05_%s_%s_53248x12288x4096.csv" % (rnd, tag)) for rnd in ("r1",) for tag in tags]:
+    tags = ([fmt_tag + "_wide"] if wide else []) + [fmt_tag]  # 256 x 512 pair tiles have their own capture
+    for tag in tags:
+        path = os.path.join(ROOT, "profiles", "gemm_tcgen05_%s_%s_53248x12288x4096.csv" % (PROFILE_ROUND, tag))
         if not os.path.exists(path):
             continue
         vals = {}
@@ -217,7 +247,7 @@ def profile_of_largest_gemm(config, fmt_tag, impl):
             act = vals.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", ("%", "nan"))[1]
         except (KeyError, ValueError):
             continue
-        return {"traffic": int(rd + wr),
+        return {"traffic": int(rd + wr), "profile_round": PROFILE_ROUND,
                 "note": "%s: one isolated launch of the QKV GEMM of a 53248-position pass under ncu --set full; "
                         "sm__pipe_tensor_cycles_active %s %%; traffic = its dram read + write bytes" % (os.path.relpath(path, ROOT), act)}
     return None
@@ -226,160 +256,313 @@ def profile_of_largest_gemm(config, fmt_tag, impl):
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Dist:
+    """Process-group plumbing (torch.distributed over NCCL) + the library's own communicator for the data path."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = env_int("WORLD_SIZE", 1)
+        self.rank = env_int("RANK", 0)
+        self.local_rank = env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200 GPU: zett_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.comm = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            from zett_b200 import parallel
+            self.comm = parallel.NativeComm.from_torch_distributed()   # zett_comm_init: ncclCommInitRank under the C ABI
+            self.side = torch.cuda.Stream(device=self.dev)
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, want_e2e=True, want_parity=True, steps=None):
+    """One workload on every rank: resident-input throughput (`value`), end-to-end throughput from host token strings
+    (`e2e`), the GEMM roofline figure, clocks, and parity of the timed output against the oracle."""
     import torch
-    import torch.distributed as dist
     import zett_synthetic as synthetic
-from zett_b200 import parallel
+    from oracle import hypernet_oracle as ho   # the checker: never on the timed path
+    from zett_b200 import parallel
     from zett_b200.modeling_hypernet import NativeHypernet
     from zett_b200.surface_forms import get_surface_form_matrix
+    from zett_b200.transfer import TokenPipeline
 
-    world = env_int("WORLD_SIZE", 1)
-    rank = env_int("RANK", 0)
-    local_rank = env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200 GPU: zett_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.config]
-    rows = args.rows or wl["rows"]
-    cfg, hn, tokens = build_workload(args.config, rank, rows)
+    world, rank, dev = d.world, d.rank, d.dev
+    steps = steps or args.steps
+    wl = WORKLOADS[name]
+    rows = rows or args.rows or wl["rows"]
+    old_env = {}
+    for k, v in (env or {}).items():
+        old_env[k] = os.environ.get(k)
+        os.environ[k] = v
+    cfg, hn, tokens = build_workload(name, rank, rows, vocab=vocab, hn_kind=hn_kind)
     lang = wl["lang"]
     weights = synthetic.make_weights(cfg, seed=0)
     nat = NativeHypernet(cfg, weights, dev, max_rows_per_pass=args.rows_per_pass, gemm_impl=args.gemm_impl,
                          split_terms=args.split_terms)  # C-ABI handle
-    del weights
-    src = torch.from_numpy(synthetic.make_source_embeddings(cfg, seed=100)).to(dev)
+    for k, v in old_env.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    src_np = synthetic.make_source_embeddings(cfg, seed=100)
+    src = torch.from_numpy(src_np).to(dev)
     D, separate = cfg.n_embd, bool(cfg.separate_out_embeddings)
     width = parallel.packed_width(D, separate)
     lang_i = -1 if lang is None else lang
+    P = args.rows_per_pass or 16384
 
     sf_host, n_trunc = get_surface_form_matrix(tokens, cfg.hn_surface_maxlen, hn)
     hist = synthetic.length_histogram(sf_host, cfg.pad_token_id)
     sf_dev = torch.from_numpy(sf_host).to(dev)
-    block = torch.zeros((rows, width), dtype=torch.float32, device=dev)
-    full = torch.empty((world * rows, width), dtype=torch.float32, device=dev) if world > 1 else block
+    # super-blocks of world * P rows: rank r owns the r-th slice of each (zett_b200/parallel.py); every rank holds `rows` rows
+    plan = parallel.shard_plan(world * rows, world, P)
+    full = torch.zeros((plan[-1][0] + world * plan[-1][1], width), dtype=torch.float32, device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    def slot_of(base, per, n_here):
+        return full[base + rank * per: base + rank * per + n_here]
 
     def forward_resident():
-        nat.forward_into(sf_dev, src, lang_i, block[:, 0:], block[:, D:] if separate else None,
-                         block[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
+        loc = 0
+        for base, per in plan:
+            n_here = min(per, rows - loc)
+            slot = slot_of(base, per, n_here)
+            nat.forward_into(sf_dev[loc:loc + n_here], src, lang_i, slot[:, 0:], slot[:, D:] if separate else None,
+                             slot[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
+            if world > 1:   # in-place all-gather of this super-block on the side stream, under the next one's compute
+                ev = torch.cuda.Event()
+                ev.record(main_stream)
+                d.side.wait_event(ev)
+                d.comm.allgather_rows(full[base: base + world * per], per, stream=d.side)
+            loc += n_here
         if world > 1:
-            dist.all_gather_into_tensor(full, block)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            main_stream.wait_stream(d.side)
 
     # ---- device-resident throughput ("value") ----------------------------------------------------------------------
     nat.set_timing(True)
     for _ in range(max(args.warmup, 3)):
         forward_resident()
     nat.check()
-    sync_all()
-    sampler = ClockSampler(local_rank)
+    d.sync_all()
+    sampler = ClockSampler(d.local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gemm_ms, gemm_flops, launches = 0.0, 0.0, 0
-    sync_all()
+    d.sync_all()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         forward_resident()
     e1.record()
-    sync_all()
-    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+    d.sync_all()
+    elapsed_ms = d.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     nat.check()
-    st = nat.stats()  # statistics of the last step
-    gemm_ms, gemm_flops, launches = st["gemm_ms"], st["flops_executed"], st["kernel_launches"]
-    ms_per_step = elapsed_ms / args.steps
+    st = nat.stats()  # statistics of the last forward_into (the last pass of the step)
+    ms_per_step = elapsed_ms / steps
     value = world * rows / (ms_per_step * 1e-3)
     terms = int(st["split_terms"])
     fmt = {3: ("bf16x3->f32", "bf16x3", 3.0), 2: ("f16+2xe5m2->f32", "f16f8", 2.0), 1: ("bf16->f32", "bf16", 1.0)}[terms]
+    # GEMM time / FLOPs / launches of one whole step: one more, untimed, step with a check after every pass
+    gemm_ms = gemm_flops = 0.0
+    launches = gemm_launches = distinct_ids = distinct_pairs = positions = 0
+    loc = 0
+    for base, per in plan:
+        n_here = min(per, rows - loc)
+        slot = slot_of(base, per, n_here)
+        nat.forward_into(sf_dev[loc:loc + n_here], src, lang_i, slot[:, 0:], slot[:, D:] if separate else None,
+                         slot[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
+        nat.check()
+        s1 = nat.stats()
+        gemm_ms += s1["gemm_ms"]; gemm_flops += s1["flops_executed"]; launches += s1["kernel_launches"]
+        gemm_launches += s1["gemm_launches"]; distinct_ids += s1["distinct_ids"]; distinct_pairs += s1["distinct_pairs"]
+        positions += s1["encoder_positions"]
+        loc += n_here
+    nat.set_timing(False)
+
+    # ---- parity of the TIMED output (SURVEY 8d: <= 1e-3 Frobenius and worst row against the fp32 oracle) ------------
+    parity = None
+    if want_parity:
+        rng = np.random.default_rng(1234 + rank)
+        pick = np.sort(rng.choice(rows, size=min(args.parity_rows, rows), replace=False))
+        glob = np.empty_like(pick)     # row of `full` holding local row i
+        loc = 0
+        for base, per in plan:
+            n_here = min(per, rows - loc)
+            m = (pick >= loc) & (pick < loc + n_here)
+            glob[m] = base + rank * per + (pick[m] - loc)
+            loc += n_here
+        got = full[torch.from_numpy(glob).to(dev)].cpu().numpy()
+        want = ho.hypernet_forward(cfg, weights, sf_host[pick], src_np, lang_index=lang)
+        masked = ho.fully_masked_rows(cfg, sf_host[pick])
+        cols = [("pred_in", got[:, :D], want[0])]
+        if separate:
+            cols.append(("pred_out", got[:, D:2 * D], want[1]))
+        cols.append(("pred_bias", got[:, (2 if separate else 1) * D], want[2]))
+        fro = worst = 0.0
+        for _, g, w in cols:
+            f, wr = ho.rel_errors(g, w, exclude=masked)
+            fro, worst = max(fro, f), max(worst, wr)
+        parity = {"fro": fro, "worst_row": worst, "rows": int(len(pick)), "budget": 1e-3, "ok": bool(fro < 1e-3 and worst < 1e-3),
+                  "against": "oracle/hypernet_oracle.py (numpy fp32 restatement pinned to reference-minted goldens) on rows "
+                             "sampled from the timed output"}
+        if world > 1:
+            # every rank recomputes 64 rows of its NEIGHBOUR's shard and holds them against the gathered matrix: bit-exact
+            nb = (rank + 1) % world
+            _, _, nb_tokens = build_workload(name, nb, rows, vocab=vocab, hn_kind=hn_kind)
+            a = int(rng.integers(0, max(1, rows - 64)))
+            nb_sf, _ = get_surface_form_matrix(nb_tokens[a:a + 64], cfg.hn_surface_maxlen, hn)
+            blk = torch.zeros((len(nb_sf), width), dtype=torch.float32, device=dev)
+            nat.forward_into(torch.from_numpy(nb_sf).to(dev), src, lang_i, blk[:, 0:], blk[:, D:] if separate else None,
+                             blk[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
+            nat.check()
+            loc, same = 0, None
+            for base, per in plan:
+                n_here = min(per, rows - loc)
+                lo, hi = max(a, loc), min(a + len(nb_sf), loc + n_here)
+                if hi > lo:
+                    theirs = full[base + nb * per + (lo - loc): base + nb * per + (hi - loc)]
+                    ok = bool(torch.equal(theirs[:, :(2 if separate else 1) * D + 1], blk[lo - a:hi - a, :(2 if separate else 1) * D + 1]))
+                    same = ok if same is None else (same and ok)
+                loc += n_here
+            t = torch.tensor([1 if same else 0], device=dev)
+            d.dist.all_reduce(t, op=d.dist.ReduceOp.MIN)
+            parity["neighbour_rows_bit_exact"] = bool(t.item() == 1)
+            parity["ok"] = bool(parity["ok"] and parity["neighbour_rows_bit_exact"])
+    del weights
 
     # ---- end to end from host token strings ("e2e") -----------------------------------------------------------------
-    nat.set_timing(False)
-    from zett_b200.transfer import TokenPipeline
-    pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=args.rows_per_pass or 16384)
+    e2e = None
+    if want_e2e:
+        pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=P)
 
-    def gather(blk):
-        if world > 1:
-            dist.all_gather_into_tensor(full, blk)                               # the single collective
+        def e2e_step():
+            # host token strings -> native retokenizer -> pinned H2D -> forward into this rank's slots -> in-place all-gather
+            # per super-block on the side stream -> pinned D2H of this rank's rows; all of it pipelined per pass
+            return pipe.run(tokens, comm=d.comm if world > 1 else None, full=full, plan=plan, rank=rank, side=getattr(d, "side", None))
 
-    def e2e_step():
-        # host token strings -> native retokenizer -> pinned H2D -> forward -> (all-gather) -> pinned D2H of this rank's
-        # rows; passes are pipelined (host retokenisation and D2H of pass k overlap the compute of pass k + 1)
-        return pipe.run(tokens, after_compute=gather)
-
-    e2e_step()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
         e2e_step()
-    sync_all()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    e2e_value = world * rows / e2e_s
-    out_pinned, sf_e2e, _ = e2e_step()
-    assert np.isfinite(out_pinned.numpy()[:, : (2 if separate else 1) * D + 1]).all()
-    assert np.array_equal(sf_e2e, sf_host)
+        d.sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        d.sync_all()
+        e2e_s = d.max_over_ranks(time.perf_counter() - t0) / steps
+        out_pinned, sf_e2e, _ = e2e_step()
+        assert np.isfinite(out_pinned.numpy()[:, : (2 if separate else 1) * D + 1]).all()
+        assert np.array_equal(sf_e2e, sf_host)
+        e2e = {"value": world * rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(world * rows * cfg.hn_surface_maxlen * 4),
+               "d2h_bytes_per_step": int(world * rows * width * 4), "ms_per_step": e2e_s * 1e3}
+    nat.close()
+    del src, sf_dev, full
+    torch.cuda.empty_cache()
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     peaks = measured_peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     f_ref = cfg.flops_per_row(pruned=False)
-    line = {
-        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": fmt[0], "data": "synthetic",
+    res = {
+        "value": value, "ms_per_step": ms_per_step, "dtype": fmt[0], "e2e": e2e, "clocks": clocks, "parity": parity,
+        "gpu_launches": int(launches * steps),
         "config": {
-            "workload": wl["workload"], "rows_per_gpu": rows, "total_rows": world * rows, "parallelism": "rows x%d" % world,
-            "hn_tokenizer": wl["hn"] + " 32k synthetic", "nonpad_length_histogram": hist, "truncated": n_trunc,
+            "workload": wl["workload"] + ("" if vocab == "random" else " [target vocabulary: concatenations of hn pieces]"),
+            "rows_per_gpu": rows, "total_rows": world * rows, "parallelism": "rows x%d" % world,
+            "hn_tokenizer": (hn_kind or wl["hn"]) + " 32k synthetic", "nonpad_length_histogram": hist, "truncated": n_trunc,
             "l2": "inputs larger than L2 (weights + per-pass activations are GBs; nothing is re-read from a warm L2 by design)",
-            "gemm_impl": int(st["gemm_impl"]), "split_terms": terms, "rows_per_pass": args.rows_per_pass or 16384,
-            "distinct_ids_per_step": int(st["distinct_ids"]), "distinct_id_position_pairs_per_step": int(st["distinct_pairs"]),
-            "packed_positions_per_step": int(st["encoder_positions"]),
+            "gemm_impl": int(st["gemm_impl"]), "split_terms": terms, "rows_per_pass": P,
+            "distinct_ids_per_step": int(distinct_ids), "distinct_id_position_pairs_per_step": int(distinct_pairs),
+            "packed_positions_per_step": int(positions),
             "dense_gflop_per_row_reference": f_ref / 1e9,
             "executed_gflop_per_row": gemm_flops / rows / 1e9 if gemm_flops else None,
         },
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": int(world * rows * cfg.hn_surface_maxlen * 4),
-                "d2h_bytes_per_step": int(world * rows * width * 4), "ms_per_step": e2e_s * 1e3},
-        "gpu_launches": int(launches * args.steps),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
                      "kernel": "gemm_tcgen05_kernel", "peak_source": peaks["src"],
                      "note": "achieved = FLOPs of the GEMMs issued in one step (each product counted once although the operand "
                              "format issues several MMA terms per product) / summed CUDA-event time of those launches",
-                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": st["gemm_launches"],
+                     "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": gemm_launches,
                      "mma_issue_tflops_f16_equivalent": (achieved * fmt[2]) if achieved else None},
     }
-    prof = profile_of_largest_gemm(args.config, fmt[1], int(st["gemm_impl"]))
+    prof = profile_of_largest_gemm(name, fmt[1], int(st["gemm_impl"]) == 5)
     if prof:
-        line["roofline"]["traffic"] = prof["traffic"]
-        line["roofline"]["profile"] = prof["note"]
+        res["roofline"]["traffic"] = prof["traffic"]
+        res["roofline"]["profile"] = prof["note"]
+    return res
+
+
+def slim(res):
+    """An `extra` entry: the figures of a secondary workload without the long config block."""
+    keep = ("rows_per_gpu", "total_rows", "workload", "hn_tokenizer", "distinct_ids_per_step", "distinct_id_position_pairs_per_step",
+            "packed_positions_per_step", "executed_gflop_per_row", "split_terms", "gemm_impl")
+    return {"value": res["value"], "unit": "rows/s", "ms_per_step": res["ms_per_step"], "e2e": res["e2e"], "clocks": res["clocks"],
+            "parity": res["parity"], "roofline": {k: res["roofline"][k] for k in ("achieved", "peak", "frac", "gemm_ms_per_step")},
+            "config": {k: res["config"][k] for k in keep}}
+
+
+def run_ours(args):
+    d = Dist()
+    world, rank = d.world, d.rank
+    main = measure(d, args.config, args)
+    extra = {}
+    if not args.no_extra:
+        if world == 1:
+            # the other single-GPU configurations of BASELINE.json, in the same run
+            for other in ("xlmr", "tinyllama", "mistral"):
+                if other != args.config:
+                    extra[other] = slim(measure(d, other, args, steps=max(3, args.steps)))
+            # how much the headline leans on the de-duplication the synthetic vocabulary allows
+            extra["%s_all_distinct" % args.config] = slim(measure(
+                d, args.config, args, env={"ZETT_DEDUP_IDS": "0", "ZETT_DEDUP_PAIRS": "0"}, want_e2e=False, want_parity=False, steps=2))
+            extra["%s_all_distinct" % args.config]["what"] = ("same workload with both de-duplications switched off (input projection per "
+                                                              "position, first encoder layer per position): every position pays full price")
+            extra["%s_concat_vocab_unigram_hn" % args.config] = slim(measure(
+                d, args.config, args, vocab="concat", hn_kind="unigram", want_e2e=False, steps=2))
+            extra["%s_concat_vocab_unigram_hn" % args.config]["what"] = (
+                "target vocabulary built from concatenations of pieces of a Unigram hn tokenizer: ids spread over the whole source "
+                "table (see distinct_ids_per_step), de-duplication on")
+        if world == 8 and args.config == "mistral":
+            # BASELINE.json configs[4]: Mistral-7B hypernet, synthetic 256k vocabulary row-sharded across 8 GPUs
+            extra["mistral_256k_vocab_8gpu"] = slim(measure(d, "mistral", args, rows=32768, steps=max(3, args.steps)))
+            extra["mistral_256k_vocab_8gpu"]["what"] = "BASELINE.json configs[4]: 262 144 rows, 32 768 per GPU, all-gather per super-block"
+    if rank != 0:
+        d.close()
+        return
+    line = {
+        "metric": METRIC, "value": main["value"], "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": main["dtype"], "data": "synthetic", "config": main["config"], "clocks": main["clocks"], "e2e": main["e2e"],
+        "gpu_launches": main["gpu_launches"], "roofline": main["roofline"], "parity": main["parity"],
+    }
+    if extra:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args.config, 1, 1, budget_s=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "rows/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line["cpu_baseline"] = {"value": r["value"], "unit": "rows/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         try:
-            line["torch_eager_b200"] = torch_eager_gpu_run(args.config, dev)
+            line["torch_eager_b200"] = torch_eager_gpu_run(args.config, d.dev)
         except Exception as e:  # noqa: BLE001
             line["torch_eager_b200"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    d.close()
 
 
 def main():
@@ -394,6 +577,8 @@ def main():
     ap.add_argument("--gemm-impl", type=int, default=0)
     ap.add_argument("--split-terms", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads of the `extra` block")
+    ap.add_argument("--parity-rows", type=int, default=128)
     ap.add_argument("--cpu-seconds", type=float, default=30.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -41,8 +41,9 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kLineBytes = 128;
 constexpr uint32_t kABytes = kBlockM * kLineBytes;        // A part of a stage: 16 KB
 constexpr uint32_t kStagingBytes = kEpilogueWarps * 4096; // per-warp transpose tiles
-constexpr int kProfSlots = 8;        // per CTA: 0 total, 1 producer empty-wait, 2 MMA full-wait, 3 MMA accumulator-wait,
-                                     //          4 epilogue accumulator-wait (warp 2), 5 epilogue busy (warp 2), 6 tiles
+constexpr int kProfSlots = 12;       // per CTA: 0 total, 1 producer empty-wait, 2 MMA full-wait, 3 MMA accumulator-wait,
+                                     //          4 epilogue accumulator-wait (warp 2), 5 epilogue busy (warp 2), 6 tiles,
+                                     //          7 epilogue tcgen05.ld wait, 8 staging stores, 9 quads (warp 2)
 
 struct GemmShape {
   int m_host;          // rows of A / out when m_dev == nullptr
@@ -122,27 +123,88 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 
 // One 32-row x 32-column accumulator chunk, second half of its trip: the rows the warp's threads hold (tcgen05.ld layout:
 // one row per thread) have been written to the warp's staging tile; lane l now takes the quads (row 4 i + l / 8, columns
-// 4 (l % 8) ..) for i = 0..7.  The loop is rolled in two halves of four quads: fully unrolled (with both GELUs inlined) the
-// epilogue alone was ~60 KB of SASS per activation, far beyond the instruction cache, and the K = 768 GEMMs of the XLM-R
-// shape ran at the speed of instruction fetch (epilogue busy 90 % of the kernel, the tensor pipe waiting for accumulators).
-template <int ACT>
+// 4 (l % 8) ..) for i = 0..7.  The epilogue shares the SM's four issue ports with nothing else, and with K = 768 (XLM-R
+// shape) a tile's main loop is only ~12 000 cycles long, so this loop is written for instruction count: the outputs a
+// GEMM produces (fp32 and / or operand lines) and its activation are template parameters, row pointers advance by
+// constants, and the loop is rolled in two halves of four quads (fully unrolled with both GELUs inlined the epilogue was
+// ~60 KB of SASS per activation -- instruction-cache misses on top).
+template <int ACT, bool F32, bool OP>
 __device__ __forceinline__ void epilogue_quads(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col,
                                                const QuadConsts& q, uint32_t& bad) {
   const int jj = lane & 7, rsub = lane >> 3;
+  const long long row = row0 + rsub;                    // this lane's rows are row, row + 4, ..., row + 28
+  const int n_rows = static_cast<int>(min(static_cast<long long>(32), static_cast<long long>(M) - row));   // valid while 4 i < n_rows
+  float* po = F32 ? ep.out_f32 + row * ep.ld_out + col : nullptr;
+  const float* pr = ep.residual ? ep.residual + row * ep.ld_res + col : nullptr;
+  int e = 0;
+  uint8_t* pl = nullptr;
+  if (OP) pl = operand_line(ep.out_op, row, col, e);
+  const bool scaled = ep.w_scale != nullptr || ep.bias != nullptr;
+  const bool affine = ep.col_scale != nullptr;
+  const int fmt = ep.out_op.fmt;
+  uint32_t rd = stg + static_cast<uint32_t>(rsub) * 128u;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     float4 x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int rr = 16 * half + 4 * i + rsub;
-      x[i] = ld_shared_v4(stg + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(jj ^ (rr & 7)) << 4));
+      const int rr = 4 * i + rsub;                       // (16 * half does not change rr & 7)
+      x[i] = ld_shared_v4(rd + static_cast<uint32_t>(4 * i) * 128u + (static_cast<uint32_t>(jj ^ (rr & 7)) << 4));
     }
+    rd += 16u * 128u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long row = row0 + 16 * half + 4 * i + rsub;
-      if (row < M) epilogue_quad<ACT>(ep, row, col, x[i], q, bad);
+      if (16 * half + 4 * i < n_rows) {
+        float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        if (scaled) {
+          v[0] = fmaf(v[0], q.ws.x, q.b.x); v[1] = fmaf(v[1], q.ws.y, q.b.y);
+          v[2] = fmaf(v[2], q.ws.z, q.b.z); v[3] = fmaf(v[3], q.ws.w, q.b.w);
+        }
+        if (ACT == kActGeluTanh) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_f(v[j]);
+        } else if (ACT == kActGeluErf) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = gelu_erf_f(v[j]);
+        }
+        if (pr) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(pr));
+          v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+        }
+        if (affine) {  // Rescaler: w * y + b with two roundings, as torch evaluates it (modeling_hypernet.py:18-19)
+          v[0] = __fadd_rn(__fmul_rn(q.cs.x, v[0]), q.ct.x); v[1] = __fadd_rn(__fmul_rn(q.cs.y, v[1]), q.ct.y);
+          v[2] = __fadd_rn(__fmul_rn(q.cs.z, v[2]), q.ct.z); v[3] = __fadd_rn(__fmul_rn(q.cs.w, v[3]), q.ct.w);
+        }
+        if (F32) {
+          const float4 y = make_float4(v[0], v[1], v[2], v[3]);
+          if (ep.stream_f32) __stcs(reinterpret_cast<float4*>(po), y); else *reinterpret_cast<float4*>(po) = y;
+        }
+        if (OP) {
+          const Packed4 p = pack_operand4(v, fmt, false, bad);
+          *reinterpret_cast<uint2*>(pl + 2 * e) = p.m;
+          if (fmt == kFmtF16F8) {
+            *reinterpret_cast<uint32_t*>(pl + 64 + e) = p.s.x;
+            *reinterpret_cast<uint32_t*>(pl + 96 + e) = p.t;
+          } else if (fmt == kFmtBf16x3) {
+            *reinterpret_cast<uint2*>(pl + 64 + 2 * e) = p.s;
+          }
+        }
+      }
+      if (F32) po += 4 * ep.ld_out;
+      if (pr) pr += 4 * ep.ld_res;
+      if (OP) pl += 4 * ep.out_op.ld_bytes;
     }
   }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_quads_mode(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col,
+                                                    const QuadConsts& q, uint32_t& bad) {
+  const bool f32 = ep.out_f32 != nullptr, op = ep.out_op.base != nullptr;
+  if (f32 && !op) epilogue_quads<ACT, true, false>(ep, stg, lane, row0, M, col, q, bad);
+  else if (!f32 && op) epilogue_quads<ACT, false, true>(ep, stg, lane, row0, M, col, q, bad);
+  else if (f32 && op) epilogue_quads<ACT, true, true>(ep, stg, lane, row0, M, col, q, bad);
+  else epilogue_quads<ACT, false, false>(ep, stg, lane, row0, M, col, q, bad);   // timing probe: arithmetic, no stores
 }
 
 // tmap_a: box {128 B, 128 rows} over A's lines;  tmap_b: box {128 B, HALVES * block_n / 2 rows} over W's lines
@@ -287,7 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int group = (warp - 2) >> 2;   // 0 or 1
     const uint32_t stg = stg_base + static_cast<uint32_t>(warp - 2) * 4096u;
     uint32_t bad = 0;
-    long long waited = 0, busy = 0;
+    long long waited = 0, busy = 0, t_ldwait = 0, t_stage = 0, t_quads = 0;
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
@@ -313,24 +375,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float v[32];
       const uint32_t wr = stg + static_cast<uint32_t>(lane) * 128u;
       const uint32_t sw = static_cast<uint32_t>(lane & 7);
-      if (c_first < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c_first), v);
+      // the per-column constants of a chunk (bias, weight scale, affine) are fetched one chunk ahead: with the shared-memory
+      // carve-out at its maximum there is next to no L1, so every one of these loads is an L2 round trip
+      QuadConsts q_next;
+      int col_next = gcol(c_first) + 4 * (lane & 7);
+      if (c_first < s.block_n) {
+        tmem_ld_32x32(taddr + static_cast<uint32_t>(c_first), v);
+        if (col_next < s.n) q_next = load_quad_consts(ep, col_next);
+      }
 #pragma unroll 1
       for (int c = c_first; c < s.block_n; c += c_step) {
+        const long long p0 = prof ? clock64() : 0;
         tmem_ld_wait();
+        const long long p1 = prof ? clock64() : 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_shared_v4(wr + ((static_cast<uint32_t>(j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        if (c + c_step < s.block_n) tmem_ld_32x32(taddr + static_cast<uint32_t>(c + c_step), v);
-        const int col = gcol(c) + 4 * (lane & 7);
-        const bool col_ok = col < s.n;
-        QuadConsts q;
-        if (col_ok) q = load_quad_consts(ep, col);
+        const QuadConsts q = q_next;
+        const int col = col_next;
+        if (c + c_step < s.block_n) {
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c + c_step), v);
+          col_next = gcol(c + c_step) + 4 * (lane & 7);
+          if (col_next < s.n) q_next = load_quad_consts(ep, col_next);
+        }
         __syncwarp();
-        if (col_ok) {
-          if (ep.act == kActGeluErf) epilogue_quads<kActGeluErf>(ep, stg, lane, row0, M, col, q, bad);
-          else if (ep.act == kActGeluTanh) epilogue_quads<kActGeluTanh>(ep, stg, lane, row0, M, col, q, bad);
-          else epilogue_quads<kActNone>(ep, stg, lane, row0, M, col, q, bad);
+        const long long p2 = prof ? clock64() : 0;
+        if (col < s.n) {
+          if (ep.act == kActGeluErf) epilogue_quads_mode<kActGeluErf>(ep, stg, lane, row0, M, col, q, bad);
+          else if (ep.act == kActGeluTanh) epilogue_quads_mode<kActGeluTanh>(ep, stg, lane, row0, M, col, q, bad);
+          else epilogue_quads_mode<kActNone>(ep, stg, lane, row0, M, col, q, bad);
         }
         __syncwarp();  // the staging tile is rewritten by the next chunk
+        if (prof) { t_ldwait += p1 - p0; t_stage += p2 - p1; t_quads += clock64() - p2; }
       }
       tc_fence_before();
       __syncwarp();
@@ -342,6 +417,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 4] = static_cast<unsigned long long>(waited);
       s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 5] = static_cast<unsigned long long>(busy);
       s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 6] = static_cast<unsigned long long>(iter);
+      s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 7] = static_cast<unsigned long long>(t_ldwait);
+      s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 8] = static_cast<unsigned long long>(t_stage);
+      s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 9] = static_cast<unsigned long long>(t_quads);
     }
   }
 

@@ -334,9 +334,10 @@ struct GemmEngine {
     const double n = last_ctas, nl = std::max(1, last_ctas / 2);
     snprintf(buf, sizeof buf,
              "{\"halves\": %d, \"stages\": %d, \"block_n\": %d, \"ctas\": %d, \"cycles_total\": %.0f, \"producer_wait_empty\": %.0f, "
-             "\"mma_wait_full\": %.0f, \"mma_wait_acc\": %.0f, \"epi_wait_acc\": %.0f, \"epi_busy\": %.0f, \"tiles_per_cta\": %.1f}",
+             "\"mma_wait_full\": %.0f, \"mma_wait_acc\": %.0f, \"epi_wait_acc\": %.0f, \"epi_busy\": %.0f, \"tiles_per_cta\": %.1f, "
+             "\"epi_ld_wait\": %.0f, \"epi_stage\": %.0f, \"epi_quads\": %.0f}",
              last_halves, last_stages, last_block_n, last_ctas, sum[0] / n, sum[1] / n, sum[2] / nl, sum[3] / nl, sum[4] / n, sum[5] / n,
-             sum[6] / n);
+             sum[6] / n, sum[7] / n, sum[8] / n, sum[9] / n);
     return buf;
   }
 };
@@ -487,6 +488,7 @@ struct zett_hn {
   zett_hn_stats stats{};
   double coef_t1 = 0, coef_t2 = 0, coef_rows = 0, coef_u = 0, coef_p = 0;  // FLOPs per surface position / encoder position / row / distinct id / distinct pair
   bool dedup_pairs = true;     // first encoder layer: LayerNorm + query/key/value once per distinct (id, position) pair
+  bool dedup_ids = true;       // input projection once per distinct id (ZETT_DEDUP_IDS=0 switches both de-duplications off)
   bool auto_terms = true;      // split_terms was left at 0: the caller accepts a fallback to the bf16 split
   std::vector<LinearW*> linears() {
     std::vector<LinearW*> v = {&in_proj0, &in_proj1.dense1, &in_proj1.dense2, &head_in.dense1, &head_in.dense2, &out_in};
@@ -525,7 +527,7 @@ size_t workspace_bytes_for(const zett_hn* h, long long rows) {
   const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
   b += sizeof(int) * (static_cast<size_t>(kMaxPassSlots) * kCntSlots + 2 * (rows + 1) + 6 * t1 + rows + t2 + 2 * n_ids) + t2;
   b += sizeof(int) * (2 * n_ids * h->L + 2 * (t1 + 1) + t2 + rows);  // distinct (id, position) pairs, per-row counts
-  b += static_cast<size_t>(std::min<long long>(t1, n_ids) * operand_ld_bytes(fmt, E));  // P_E
+  b += static_cast<size_t>((h->dedup_ids ? std::min<long long>(t1, n_ids) : t1) * operand_ld_bytes(fmt, E));  // P_E
   b += static_cast<size_t>(2 * t2 * operand_ld_bytes(fmt, H));                          // PH_a, PH_b
   b += static_cast<size_t>(t2 * operand_ld_bytes(fmt, I));                              // PI
   b += 4ull * t2 * H * 3 + 4ull * t2 * 3 * H;  // F1..F3, F4
@@ -567,7 +569,7 @@ int ensure_workspace(zett_hn* h, long long rows) {
   WS_ALLOC(w.tok2_row, t2);
   WS_ALLOC(w.tok2_valid, t2);
   const long long n_ids = static_cast<long long>(h->cfg.original_vocab_size) + h->n_fallback;
-  w.uniq_cap = std::min<long long>(t1, n_ids);
+  w.uniq_cap = h->dedup_ids ? std::min<long long>(t1, n_ids) : t1;
   WS_ALLOC(w.id_claim, n_ids);
   WS_ALLOC(w.id_slot, n_ids);
   WS_ALLOC(w.uniq_src, w.uniq_cap);
@@ -784,7 +786,7 @@ int forward_pass(zett_hn* h, const int32_t* ids, int rows, const float* source, 
   ZETT_CUDA(cudaMemsetAsync(w.id_claim, 0x7F, sizeof(int) * (static_cast<size_t>(h->cfg.original_vocab_size) + h->n_fallback), stream));
   PackParams pp{};
   pp.ids = ids; pp.n_rows = rows; pp.L = L; pp.pad_id = h->cfg.pad_token_id; pp.v0 = h->cfg.original_vocab_size;
-  pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.counts = counts; pp.sticky_bad = h->flags + kFlagBadId;
+  pp.n_fallback = h->n_fallback; pp.lang_slot = lang ? 1 : 0; pp.dedup_ids = h->dedup_ids ? 1 : 0; pp.counts = counts; pp.sticky_bad = h->flags + kFlagBadId;
   pp.row_cnt = w.row_cnt; pp.row_start1 = w.row_start1; pp.row_start2 = w.row_start2; pp.tok_id = w.tok_id; pp.tok_pos = w.tok_pos;
   pp.tok_enc = w.tok_enc; pp.tok1_row = w.tok1_row; pp.lang_enc = w.lang_enc; pp.tok2_row = w.tok2_row; pp.tok2_valid = w.tok2_valid;
   pp.id_claim = w.id_claim; pp.id_slot = w.id_slot; pp.uniq_src = w.uniq_src; pp.tok_u = w.tok_u;
@@ -1030,6 +1032,8 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   h->gemm.set_precision(terms == 0 ? 2 : terms);
   h->gemm.read_env();
   if (const char* e = getenv("ZETT_DEDUP_PAIRS")) h->dedup_pairs = atoi(e) != 0;
+  if (const char* e = getenv("ZETT_DEDUP_IDS")) h->dedup_ids = atoi(e) != 0;
+  if (!h->dedup_ids) h->dedup_pairs = false;   // the pair table is built on the distinct-id numbering
   if (cudaMalloc(&h->flags, sizeof(unsigned int) * kFlagSlots) != cudaSuccess || cudaMemset(h->flags, 0, sizeof(unsigned int) * kFlagSlots) != cudaSuccess) {
     delete h;
     return fail(ZETT_ERR_CUDA, "cannot allocate the handle's flag words");

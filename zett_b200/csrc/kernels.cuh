@@ -34,6 +34,7 @@ struct PackParams {
   int n_rows, L;
   int pad_id, v0, n_fallback;  // n_fallback = max(hn_n_extra_tokens, 1)
   int lang_slot;               // 1 when a lang-id position is appended to every row
+  int dedup_ids;               // 0: every position is its own "distinct id" (the all-distinct measurement, ZETT_DEDUP_IDS=0)
   int* counts;                 // [kCntSlots], zeroed before the pass
   unsigned int* sticky_bad;    // handle-wide flag, set when any id of any pass was out of range (cleared by zett_hn_check)
   int* row_cnt;                // [n_rows]      kept positions of each row
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) pack_scan_kernel(const PackPa
     warp_excl[lane] = wi - w;
     if (lane == 31) {
       p.counts[kCntSurface] = wi;
+      if (!p.dedup_ids) p.counts[kCntUnique] = wi;
       p.counts[kCntEncoder] = wi + (p.lang_slot ? p.n_rows : 0);
       p.counts[kCntRows] = p.n_rows;
       p.counts[kCntPairs] = (p.pair_claim && p.lang_slot) ? 1 : 0;  // pair 0 = the lang-id position
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(kPackBlock) pack_emit_kernel(const PackParams 
     p.tok1_row[t1 + j] = r;
     p.tok2_row[t2 + j] = r;
     p.tok2_valid[t2 + j] = static_cast<unsigned char>((nonpad >> q) & 1u);
-    atomicMin(&p.id_claim[id], t1 + j);
+    if (p.dedup_ids) atomicMin(&p.id_claim[id], t1 + j);
     if (p.pair_claim) atomicMin(&p.pair_claim[id * p.L + q], t1 + j);
     ++j;
   }
@@ -169,7 +171,9 @@ __global__ void __launch_bounds__(kPackBlock) pack_owner_kernel(const PackParams
   if (t == 0 && p.pair_claim && p.lang_slot) { p.pair_u[0] = 0; p.pair_pos[0] = 0; }  // placeholder, overwritten by the lang-id LayerNorm
   if (t >= p.counts[kCntSurface]) return;
   const int id = p.tok_id[t];
-  if (p.id_claim[id] == t) {
+  if (!p.dedup_ids) {
+    p.uniq_src[t] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
+  } else if (p.id_claim[id] == t) {
     const int u = atomicAdd(&p.counts[kCntUnique], 1);
     p.id_slot[id] = u;
     p.uniq_src[u] = (id >= p.v0) ? (-1 - (id - p.v0)) : id;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kPackBlock) pack_index_kernel(const PackParams
   if (p.pair_claim && t >= (p.lang_slot ? 1 : 0) && t < p.counts[kCntPairs]) p.pair_u[t] = p.id_slot[p.pair_u[t]];
   if (t >= p.counts[kCntSurface]) return;
   const int id = p.tok_id[t];
-  p.tok_u[t] = p.id_slot[id];
+  p.tok_u[t] = p.dedup_ids ? p.id_slot[id] : t;
   if (p.pair_claim) p.enc_pair[p.tok_enc[t]] = p.pair_slot[id * p.L + p.tok_pos[t]];
 }
 

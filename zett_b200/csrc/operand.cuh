@@ -50,29 +50,9 @@ struct OperandOut {
   unsigned int* sat;
 };
 
-// kFmtF16F8: p0 (fp16 bits) and the two e5m2 bytes of one value; `bad` is set when |x| exceeds fp16's range
-__device__ __forceinline__ void split_f16f8(float x, bool is_weight, uint16_t& p0, uint8_t& q0, uint8_t& q1, uint32_t& bad) {
-  bad |= (fabsf(x) > kF16Max) ? 1u : 0u;
-  const float xc = fminf(fmaxf(x, -kF16Max), kF16Max);
-  const __half h = __float2half_rn(xc);
-  const float lo = x - __half2float(h);
-  p0 = __half_as_ushort(h);
-  if (is_weight) {
-    q0 = __nv_cvt_float_to_fp8(x * kF8Down, __NV_SATFINITE, __NV_E5M2);
-    q1 = __nv_cvt_float_to_fp8(lo * kF8Up, __NV_SATFINITE, __NV_E5M2);
-  } else {
-    q0 = __nv_cvt_float_to_fp8(lo * kF8Up, __NV_SATFINITE, __NV_E5M2);
-    q1 = __nv_cvt_float_to_fp8(x * kF8Down, __NV_SATFINITE, __NV_E5M2);
-  }
-}
-
 __device__ __forceinline__ float e5m2_to_float(uint8_t v) {
   const __half_raw hr = __nv_cvt_fp8_to_halfraw(v, __NV_E5M2);
   return __half2float(__half(hr));
-}
-
-__device__ __forceinline__ uint32_t pack4_u8(const uint8_t* b) {
-  return uint32_t(b[0]) | (uint32_t(b[1]) << 8) | (uint32_t(b[2]) << 16) | (uint32_t(b[3]) << 24);
 }
 
 // The 16 bytes four consecutive values occupy in a line, as {main-plane 8 bytes, second 4 or 8, third 4}:
@@ -83,28 +63,38 @@ struct Packed4 {
   uint32_t t;
 };
 
+__device__ __forceinline__ uint32_t half2_bits(const __half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
+
 __device__ __forceinline__ Packed4 pack_operand4(const float* y, int fmt, bool is_weight, uint32_t& bad) {
   Packed4 r;
   r.s = make_uint2(0u, 0u);
   r.t = 0u;
   if (fmt == kFmtF16F8) {
-    uint16_t a[4];
-    uint8_t b[4], c[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_f16f8(y[i], is_weight, a[i], b[i], c[i], bad);
-    r.m.x = a[0] | (uint32_t(a[1]) << 16); r.m.y = a[2] | (uint32_t(a[3]) << 16);
-    r.s.x = pack4_u8(b);
-    r.t = pack4_u8(c);
+    // paired conversions (cvt.rn.f16x2.f32, cvt.rn.satfinite.e5m2x2.f32).  No clamp: a value beyond fp16's range is
+    // counted, and a forward that counted any is repeated in the bf16 format (zett_hn_check), so what is stored for it
+    // does not matter.
+    const float m = fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3])));
+    bad |= (m > kF16Max) ? 1u : 0u;
+    const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const float2 lo01 = make_float2((y[0] - f01.x) * kF8Up, (y[1] - f01.y) * kF8Up);
+    const float2 lo23 = make_float2((y[2] - f23.x) * kF8Up, (y[3] - f23.y) * kF8Up);
+    const float2 dn01 = make_float2(y[0] * kF8Down, y[1] * kF8Down), dn23 = make_float2(y[2] * kF8Down, y[3] * kF8Down);
+    const uint32_t lo = uint32_t(__nv_cvt_float2_to_fp8x2(lo01, __NV_SATFINITE, __NV_E5M2)) |
+                        (uint32_t(__nv_cvt_float2_to_fp8x2(lo23, __NV_SATFINITE, __NV_E5M2)) << 16);
+    const uint32_t dn = uint32_t(__nv_cvt_float2_to_fp8x2(dn01, __NV_SATFINITE, __NV_E5M2)) |
+                        (uint32_t(__nv_cvt_float2_to_fp8x2(dn23, __NV_SATFINITE, __NV_E5M2)) << 16);
+    r.m.x = half2_bits(h01); r.m.y = half2_bits(h23);
+    r.s.x = is_weight ? dn : lo;   // q0: weights 2^-6 w        activations 2^6 (x - p0)
+    r.t = is_weight ? lo : dn;     // q1: weights 2^6 (w - p0)   activations 2^-6 x
   } else {
-    uint16_t a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(y[i]);
-      a[i] = __bfloat16_as_ushort(h);
-      b[i] = __bfloat16_as_ushort(__float2bfloat16_rn(y[i] - __bfloat162float(h)));
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(y[0], y[1]), h23 = __floats2bfloat162_rn(y[2], y[3]);
+    r.m.x = *reinterpret_cast<const uint32_t*>(&h01); r.m.y = *reinterpret_cast<const uint32_t*>(&h23);
+    if (fmt == kFmtBf16x3) {
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[0] - f01.x, y[1] - f01.y), l23 = __floats2bfloat162_rn(y[2] - f23.x, y[3] - f23.y);
+      r.s.x = *reinterpret_cast<const uint32_t*>(&l01); r.s.y = *reinterpret_cast<const uint32_t*>(&l23);
     }
-    r.m.x = a[0] | (uint32_t(a[1]) << 16); r.m.y = a[2] | (uint32_t(a[3]) << 16);
-    r.s.x = b[0] | (uint32_t(b[1]) << 16); r.s.y = b[2] | (uint32_t(b[3]) << 16);
   }
   return r;
 }

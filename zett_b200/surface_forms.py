@@ -18,6 +18,19 @@ import numpy as np
 from . import _lib
 
 
+def default_threads() -> int:
+    """Worker threads of the retokenizer when the caller does not say: all cores, divided among the processes of a
+    one-process-per-GPU launch (LOCAL_WORLD_SIZE / WORLD_SIZE as torchrun sets them) so that eight ranks do not each start a
+    full-machine pool on the same host."""
+    import os
+    cores = os.cpu_count() or 1
+    try:
+        local = int(os.environ.get("LOCAL_WORLD_SIZE") or os.environ.get("WORLD_SIZE") or 1)
+    except ValueError:
+        local = 1
+    return max(1, cores // max(1, local))
+
+
 class NativeTokenizerModel:
     """A ``zett_tok`` handle: the Unigram / BPE model of an hn tokenizer."""
 
@@ -89,6 +102,8 @@ class NativeTokenizerModel:
         tokenizer's special tokens.  The vocabulary crosses the ABI as ONE NUL-separated buffer: marshalling 50k strings
         into a ``char*`` array costs twice the retokenisation itself."""
         v = len(tokens)
+        if n_threads <= 0:
+            n_threads = default_threads()
         out = np.empty((v + padding, maxlen), dtype=np.int32)
         out_p = out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
         n_trunc = ctypes.c_int64(0)

@@ -241,47 +241,62 @@ class TokenPipeline:
         self.out_pinned = torch.empty((n_rows, width), dtype=torch.float32, pin_memory=True)
         self._cap = n_rows
 
-    def run(self, tokens, after_compute=None):
+    def run(self, tokens, after_compute=None, comm=None, full=None, plan=None, rank: int = 0, side=None):
         """Returns ``(out_pinned[:n] as [n, n_out * D + 4] fp32, surface_forms [n, L] int32, n_truncated)``; columns
-        are ``pred_in | pred_out | bias`` (``zett_b200.parallel.unpack`` splits them).  ``after_compute(block)`` runs on
-        the compute stream after the last pass (the all-gather of the multi-GPU path).  Like ``ZettHypernet.forward`` the
-        call raises ``IndexError`` for an out-of-range id in ANY pass (the library's flag is sticky across passes) and
-        repeats itself with the bf16 operand split when a value left fp16's range (single-process use only: a collective
-        in ``after_compute`` must not be repeated by one rank alone)."""
+        are ``pred_in | pred_out | bias`` (``zett_b200.parallel.unpack`` splits them).
+
+        Multi-GPU use: ``plan`` = ``parallel.shard_plan(world * n, world, rows_per_pass)``, ``full`` = the padded full matrix
+        on this device, ``comm`` = a ``parallel.NativeComm``, ``side`` = a CUDA stream: pass k is computed straight into this
+        rank's slot of super-block k and the in-place all-gather of that super-block runs on ``side`` under the compute of
+        pass k + 1.  ``after_compute(block)`` (single-GPU callers) runs on the compute stream after the last pass.
+
+        Like ``ZettHypernet.forward`` the call raises ``IndexError`` for an out-of-range id in ANY pass (the library's flag
+        is sticky across passes) and repeats itself with the bf16 operand split when a value left fp16's range
+        (single-process use only: a collective must not be repeated by one rank alone)."""
         result = {}
 
         def enqueue():
-            result["v"] = self._run_once(tokens, after_compute)
+            result["v"] = self._run_once(tokens, after_compute, comm, full, plan, rank, side)
 
-        self.nat.run_checked(enqueue, allow_fallback=after_compute is None)
+        self.nat.run_checked(enqueue, allow_fallback=after_compute is None and comm is None)
         self.copy_stream.synchronize()
         return result["v"]
 
-    def _run_once(self, tokens, after_compute=None):
+    def _run_once(self, tokens, after_compute=None, comm=None, full=None, plan=None, rank=0, side=None):
         from .parallel import packed_width
         cfg = self.cfg
         n, D, separate = len(tokens), cfg.n_embd, bool(cfg.separate_out_embeddings)
         width = packed_width(D, separate)
         self._ensure(n, width)
         stream = torch.cuda.current_stream(self.device)
-        n_trunc = 0
-        events = []
-        for lo in range(0, n, self.rows_per_pass):
-            hi = min(n, lo + self.rows_per_pass)
-            chunk = tokens[lo:hi]
-            sf, nt = self.tok_model.surface_forms(chunk, cfg.hn_surface_maxlen, self.pad_id, special_tokens=self.special)  # host
+        if plan is None:   # single GPU: a "super-block" is one pass of this rank
+            plan = [(lo, min(self.rows_per_pass, n - lo)) for lo in range(0, n, self.rows_per_pass)]
+            full, rank = self.block, 0
+        world = 1 if comm is None else comm.world
+        n_trunc, loc = 0, 0
+        for base, per in plan:
+            n_here = min(per, n - loc)
+            if n_here <= 0:
+                break
+            lo, hi = loc, loc + n_here
+            sf, nt = self.tok_model.surface_forms(tokens[lo:hi], cfg.hn_surface_maxlen, self.pad_id, special_tokens=self.special)  # host
             n_trunc += nt
             self.sf_pinned[lo:hi].numpy()[...] = sf
             self.sf_dev[lo:hi].copy_(self.sf_pinned[lo:hi], non_blocking=True)                              # H2D
-            blk = self.block[lo:hi]
+            blk = full[base + rank * per: base + rank * per + n_here]
             self.nat.forward_into(self.sf_dev[lo:hi], self.src, self.lang, blk[:, 0:], blk[:, D:] if separate else None,
                                   blk[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
             ev = torch.cuda.Event()
             ev.record(stream)
+            if comm is not None and world > 1:                                                              # all-gather
+                side.wait_event(ev)
+                comm.allgather_rows(full[base: base + world * per], per, stream=side)
             with torch.cuda.stream(self.copy_stream):                                                       # D2H
                 self.copy_stream.wait_event(ev)
                 self.out_pinned[lo:hi].copy_(blk, non_blocking=True)
-            events.append(ev)
+            loc = hi
+        if comm is not None and world > 1:
+            stream.wait_stream(side)
         if after_compute is not None:
             after_compute(self.block[:n])
         return self.out_pinned[:n], self.sf_pinned[:n].numpy(), n_trunc

@@ -207,3 +207,30 @@ def make_target_tokens(n_tokens: int, seed: int = 2, specials: Tuple[str, ...] =
 def length_histogram(surface_forms: np.ndarray, pad_token_id: int) -> List[int]:
     n = (np.asarray(surface_forms) != pad_token_id).sum(axis=1)
     return np.bincount(n, minlength=surface_forms.shape[1] + 1).tolist()
+
+
+def make_concat_tokens(n_tokens: int, hn_tokenizer, seed: int = 3, specials: Tuple[str, ...] = ("</s>",),
+                       length_p=(0.20, 0.40, 0.22, 0.10, 0.05, 0.02, 0.01)) -> List[str]:
+    """A second target vocabulary (bench.py ``extra``): every token is a concatenation of 1..7 pieces DRAWN FROM THE hn
+    TOKENIZER'S OWN VOCABULARY, so its retokenisation uses ids spread over the whole source table instead of the few short
+    pieces random strings fall apart into -- the de-duplication of the input projection / first encoder layer finds far
+    less to share.  ``length_p`` follows the non-pad length histogram of the default vocabulary."""
+    rng = np.random.default_rng(seed)
+    alphabet = [BYTES_TO_CHARS[b] for b in range(256)]
+    special = set(hn_tokenizer.all_special_tokens)
+    model = hn_tokenizer.backend_tokenizer.model
+    pieces = sorted(t for t in hn_tokenizer.get_vocab() if len(t) >= 3 and t not in special and len(model.tokenize(t)) == 1)
+    out = list(specials) + alphabet
+    seen = set(out)
+    p = np.asarray(length_p, dtype=np.float64)
+    p = p / p.sum()
+    while len(out) < n_tokens:
+        m = n_tokens - len(out)
+        ks = rng.choice(np.arange(1, len(p) + 1), size=m, p=p)
+        idx = rng.integers(0, len(pieces), size=(m, len(p)))
+        for i in range(m):
+            s = "".join(pieces[j] for j in idx[i, : ks[i]])
+            if s not in seen:
+                seen.add(s)
+                out.append(s)
+    return out[:n_tokens]
