@@ -378,26 +378,15 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
     elapsed_ms = d.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     nat.check()
-    st = nat.stats()  # statistics of the last forward_into (the last pass of the step)
+    st = nat.stats()  # totals over the `steps` timed steps (the library accumulates between two checks)
     ms_per_step = elapsed_ms / steps
     value = world * rows / (ms_per_step * 1e-3)
     terms = int(st["split_terms"])
     fmt = {3: ("bf16x3->f32", "bf16x3", 3.0), 2: ("f16+2xe5m2->f32", "f16f8", 2.0), 1: ("bf16->f32", "bf16", 1.0)}[terms]
-    # GEMM time / FLOPs / launches of one whole step: one more, untimed, step with a check after every pass
-    gemm_ms = gemm_flops = 0.0
-    launches = gemm_launches = distinct_ids = distinct_pairs = positions = 0
-    loc = 0
-    for base, per in plan:
-        n_here = min(per, rows - loc)
-        slot = slot_of(base, per, n_here)
-        nat.forward_into(sf_dev[loc:loc + n_here], src, lang_i, slot[:, 0:], slot[:, D:] if separate else None,
-                         slot[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
-        nat.check()
-        s1 = nat.stats()
-        gemm_ms += s1["gemm_ms"]; gemm_flops += s1["flops_executed"]; launches += s1["kernel_launches"]
-        gemm_launches += s1["gemm_launches"]; distinct_ids += s1["distinct_ids"]; distinct_pairs += s1["distinct_pairs"]
-        positions += s1["encoder_positions"]
-        loc += n_here
+    # GEMM time (CUDA events around every GEMM launch INSIDE the timed region), FLOPs and launches of one step
+    gemm_ms, gemm_flops = st["gemm_ms"] / steps, st["flops_executed"] / steps
+    launches, gemm_launches = st["kernel_launches"] // steps, st["gemm_launches"] // steps
+    distinct_ids, distinct_pairs, positions = st["distinct_ids"] // steps, st["distinct_pairs"] // steps, st["encoder_positions"] // steps
     nat.set_timing(False)
 
     # ---- parity of the TIMED output (<= 1e-3 Frobenius and worst row against the fp32 oracle) ------------

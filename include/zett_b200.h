@@ -127,7 +127,9 @@ int zett_hn_check(zett_hn* h, void* cuda_stream);
  * rewritten from their fp32 originals and the workspace is re-sized on the next forward.  Synchronises the device. */
 int zett_hn_set_split_terms(zett_hn* h, int split_terms);
 
-/* Execution statistics of the last forward: kernels launched, packed (non-pad) positions, rows. */
+/* Execution statistics of ALL forwards enqueued between the two most recent zett_hn_check calls (a caller that runs one
+ * forward per pass, or several steps, reads the totals after one check): kernels launched, packed (non-pad) positions,
+ * rows, GEMM FLOPs and -- with zett_hn_set_timing -- the summed device time of the GEMM launches. */
 typedef struct zett_hn_stats {
   int64_t kernel_launches;
   int64_t rows;
@@ -147,7 +149,7 @@ typedef struct zett_hn_stats {
 int zett_hn_get_stats(zett_hn* h, zett_hn_stats* out);
 
 /* enable != 0: bracket every GEMM launch with CUDA events on the caller's stream; zett_hn_check then fills
- * gemm_ms / gemm_launches of the last forward (the roofline figure of bench.py). */
+ * gemm_ms / gemm_launches of the forwards since the previous check (the roofline figure of bench.py). */
 int zett_hn_set_timing(zett_hn* h, int enable);
 
 void zett_hn_destroy(zett_hn* h);

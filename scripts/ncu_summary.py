@@ -13,7 +13,8 @@ KEEP = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
-    "l1tex__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second",
+    "l1tex__t_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_tensor.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second",
     "gpc__cycles_elapsed.avg.per_second", "dram__cycles_elapsed.avg.per_second",
 ]
 

@@ -75,3 +75,31 @@ def test_bfloat16_leaves_are_widened_exactly():
     sd = flax_params_to_state_dict(read_flax_msgpack(blob))
     want = (bf.astype(np.uint32) << 16).view(np.float32).reshape(2, 2).T
     np.testing.assert_array_equal(sd["a.weight"], want)
+
+
+def test_checkpoint_with_flax_vocab_1_word_embeddings(tmp_path):
+    """The Flax hypernet is built with vocab_size = 1: a checkpoint that carries the [1, H] word-embedding table (never
+    read on the inputs_embeds path) must load, as the reference's converter lets it (scripts/convert_to_pt.py:35-45)."""
+    cfg = synthetic.make_config("tiny")
+    weights = synthetic.make_weights(cfg, seed=3)
+    with_we = dict(weights)
+    with_we["model.embeddings.word_embeddings.weight"] = np.zeros((1, cfg.hn_hidden_size), dtype=np.float32)
+    blob = msgpack.packb(_to_flax_tree(with_we, chunk_name=None), use_bin_type=True)
+    cfg.save_pretrained(tmp_path)
+    open(os.path.join(tmp_path, "flax_model.msgpack"), "wb").write(blob)
+    model = load_flax_hypernet(str(tmp_path))
+    got = model.state_dict()
+    for k in weights:
+        if "word_embeddings" not in k:
+            np.testing.assert_array_equal(got[k].numpy(), weights[k])
+
+
+def test_msgpack_serialize_roundtrip_bias_file():
+    """bias.msgpack (scripts/transfer.py:305-310) is a bare ndarray in Flax's msgpack encoding."""
+    from zett_b200.checkpoint import msgpack_serialize
+    b = np.linspace(-1, 1, 37, dtype=np.float32)
+    back = read_flax_msgpack(msgpack_serialize(b))
+    np.testing.assert_array_equal(back, b)
+    tree = {"a": {"b": b, "c": np.arange(6, dtype=np.int32).reshape(2, 3)}}
+    back = read_flax_msgpack(msgpack_serialize(tree))
+    np.testing.assert_array_equal(back["a"]["c"], tree["a"]["c"])

@@ -173,3 +173,32 @@ def test_post_step_special_rows_and_splice(tmp_path):
     t = torch.zeros((5, 4))
     overwrite_special_rows(t, None, None, torch.ones((3, 4)), None, [2], [4])
     assert t[4].sum() == 4 and t[:4].sum() == 0
+
+
+def test_transfer_model_writes_bias_msgpack_when_the_model_has_no_bias(tmp_path, monkeypatch):
+    """scripts/transfer.py:305-310: a base model without an output-bias parameter gets the predicted bias as bias.msgpack
+    next to the saved model (Flax msgpack encoding of the bare array).  The hypernet is replaced by a stand-in here: the
+    post-step is host logic."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from zett_b200 import transfer
+    from zett_b200.checkpoint import read_flax_msgpack
+    rng = np.random.default_rng(0)
+    model = GPT2LMHeadModel(GPT2Config(vocab_size=50, n_positions=16, n_embd=32, n_layer=1, n_head=2))
+    hn = synthetic.make_hn_tokenizer("unigram", 600, seed=5)
+    target = synthetic.make_hn_tokenizer("unigram", 400, seed=6)   # stands in for a byte-level target tokenizer
+    n = len(target)
+    pred = (rng.standard_normal((n, 32)).astype(np.float32), None, rng.standard_normal(n).astype(np.float32))
+    monkeypatch.setattr(transfer, "make_predict", lambda hypernet, stacked, lang_index=None: (lambda sfm, priors=None: pred))
+
+    class Base:   # the base model's tokenizer: two special tokens that also exist in the target vocabulary
+        all_special_tokens = ["<s>", "</s>"]
+        all_special_ids = [0, 2]
+
+        def save_pretrained(self, path):
+            pass
+    hyper = type("H", (), {"config": synthetic.make_config("tiny")})()
+    out = tmp_path / "out"
+    _, info = transfer.transfer_model(hyper, model, Base(), target, hn, output=str(out))
+    assert info["bias_written_to"] == "bias.msgpack" and info["rows"] == n
+    np.testing.assert_array_equal(read_flax_msgpack(str(out / "bias.msgpack")), pred[2])
+    assert (out / "config.json").exists()

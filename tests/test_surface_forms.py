@@ -145,3 +145,92 @@ def test_blob_entry_point_equals_pointer_array(golden_dir, case):
         assert na == nb and a.shape == (len(toks), 5)
         if not any(t in spec["special_tokens"] for t in toks):
             np.testing.assert_array_equal(a, c)
+
+
+def _byte_tokens():
+    return ["<0x%02X>" % b for b in range(256)]
+
+
+def test_option_branches_against_hf():
+    """The model options the shipped hn tokenizers do not use, each against the HF wheel on randomised input: Unigram and
+    BPE byte_fallback (unknown chars become <0xXX> ids), BPE continuing_subword_prefix / end_of_word_suffix, BPE without an
+    unk token (unknown chars are dropped), ignore_merges."""
+    from tokenizers import models
+    rng = np.random.default_rng(21)
+    alphabet = ["a", "b", "c", "é", "ł", "z"]   # "z" and sometimes "ł" are outside the vocabularies below
+
+    def strings(k=200, maxlen=10):
+        for _ in range(k):
+            yield "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), size=int(rng.integers(0, maxlen))))
+
+    # --- Unigram byte_fallback
+    for trial in range(6):
+        vocab = [("<unk>", 0.0)] + [(t, 0.0) for t in _byte_tokens()]
+        for _ in range(int(rng.integers(4, 25))):
+            n = int(rng.integers(1, 4))
+            p = "".join(alphabet[int(i)] for i in rng.integers(0, 4, size=n))
+            if p not in dict(vocab):
+                vocab.append((p, float(-rng.integers(1, 6))))
+        hf = models.Unigram(vocab, unk_id=0, byte_fallback=True)
+        nat = NativeTokenizerModel.unigram(vocab, 0, byte_fallback=True)
+        for s in strings():
+            want = [t.id for t in hf.tokenize(s)] if s else []
+            assert nat.tokenize(s) == want, ("unigram byte_fallback", vocab[257:], s)
+
+    # --- BPE: byte_fallback / prefix + suffix / no unk / ignore_merges
+    def random_bpe(chars, extra_tokens=(), prefix="", suffix=""):
+        vocab = {}
+        for t in extra_tokens:
+            vocab[t] = len(vocab)
+        forms = set()
+        for ch in chars:
+            forms.update({ch, prefix + ch, ch + suffix, prefix + ch + suffix})
+        for f in sorted(forms):
+            if f not in vocab:
+                vocab[f] = len(vocab)
+        syms = [s for s in vocab if s not in extra_tokens]
+        merges = []
+        for _ in range(int(rng.integers(3, 20))):
+            a, b = syms[int(rng.integers(0, len(syms)))], syms[int(rng.integers(0, len(syms)))]
+            if prefix:
+                # HF builds the merged token as a + b[len(prefix):] unconditionally: the right part of a merge is a
+                # continuing symbol, and a symbol carrying the end-of-word suffix cannot be a left part
+                if not b.startswith(prefix) or (suffix and a.endswith(suffix)):
+                    continue
+                merged = a + b[len(prefix):]
+            else:
+                merged = a + b
+            if (a, b) in merges:
+                continue
+            merges.append((a, b))
+            if merged not in vocab:
+                vocab[merged] = len(vocab)
+                syms.append(merged)
+        return vocab, merges
+
+    for trial in range(6):
+        vocab, merges = random_bpe(alphabet[:4], extra_tokens=["<unk>"] + _byte_tokens())
+        for fuse in (False, True):
+            hf = models.BPE(vocab=vocab, merges=merges, unk_token="<unk>", fuse_unk=fuse, byte_fallback=True)
+            nat = NativeTokenizerModel.bpe(vocab, merges, unk_token="<unk>", fuse_unk=fuse, byte_fallback=True)
+            for s in strings():
+                want = [t.id for t in hf.tokenize(s)] if s else []
+                assert nat.tokenize(s) == want, ("bpe byte_fallback", fuse, merges, s)
+    for trial in range(6):
+        vocab, merges = random_bpe(alphabet[:4], extra_tokens=["<unk>"], prefix="##", suffix="</w>")
+        hf = models.BPE(vocab=vocab, merges=merges, unk_token="<unk>", continuing_subword_prefix="##", end_of_word_suffix="</w>")
+        nat = NativeTokenizerModel.bpe(vocab, merges, unk_token="<unk>", continuing_subword_prefix="##", end_of_word_suffix="</w>")
+        for s in strings():
+            want = [t.id for t in hf.tokenize(s)] if s else []
+            assert nat.tokenize(s) == want, ("bpe prefix/suffix", merges, s)
+    for trial in range(6):
+        vocab, merges = random_bpe(alphabet[:4])
+        hf = models.BPE(vocab=vocab, merges=merges)                       # no unk token: unknown chars vanish
+        nat = NativeTokenizerModel.bpe(vocab, merges)
+        hf_im = models.BPE(vocab=vocab, merges=merges, ignore_merges=True)
+        nat_im = NativeTokenizerModel.bpe(vocab, merges, ignore_merges=True)
+        for s in strings():
+            want = [t.id for t in hf.tokenize(s)] if s else []
+            assert nat.tokenize(s) == want, ("bpe no unk", merges, s)
+            want = [t.id for t in hf_im.tokenize(s)] if s else []
+            assert nat_im.tokenize(s) == want, ("bpe ignore_merges", merges, s)

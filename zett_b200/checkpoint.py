@@ -58,6 +58,27 @@ def read_flax_msgpack(path_or_bytes) -> dict:
     return _unchunk(msgpack.unpackb(raw, ext_hook=_ext_hook, raw=False, strict_map_key=False))
 
 
+def _ndarray_to_ext(a: np.ndarray) -> msgpack.ExtType:
+    a = np.ascontiguousarray(a)
+    return msgpack.ExtType(EXT_NDARRAY, msgpack.packb((list(a.shape), a.dtype.name, a.tobytes()), use_bin_type=True))
+
+
+def msgpack_serialize(tree) -> bytes:
+    """``flax.serialization.msgpack_serialize`` for a numpy array or a nested dict of them (arrays below the 2**30-byte
+    chunking threshold): what the reference writes as ``bias.msgpack`` (scripts/transfer.py:305-310)."""
+    def enc(x):
+        if isinstance(x, dict):
+            return {k: enc(v) for k, v in x.items()}
+        if isinstance(x, np.generic):
+            return msgpack.ExtType(EXT_NPSCALAR, msgpack.packb((list(np.asarray(x).shape), np.asarray(x).dtype.name, np.asarray(x).tobytes()),
+                                                               use_bin_type=True))
+        a = np.asarray(x)
+        if a.nbytes >= 2 ** 30:
+            raise ValueError("arrays of 1 GiB and more need the chunked layout, which this writer does not produce")
+        return _ndarray_to_ext(a)
+    return msgpack.packb(enc(tree), use_bin_type=True)
+
+
 def _flatten(tree, prefix=()):
     for k, v in tree.items():
         if isinstance(v, dict):
@@ -99,6 +120,10 @@ def load_flax_hypernet(checkpoint_path: str):
     config = ZettHypernetConfig.from_pretrained(checkpoint_path)
     model = ZettHypernet(config)
     sd = flax_params_to_state_dict(read_flax_msgpack(os.path.join(checkpoint_path, "flax_model.msgpack")))
+    # The Flax hypernet is built with vocab_size = 1, so a checkpoint may carry a [1, H] word-embedding table; it is never
+    # read (the forward feeds inputs_embeds) and the reference's converter tolerates the mismatch
+    # (scripts/convert_to_pt.py:35-45 goes through load_flax_weights_in_pytorch_model): drop it before checking.
+    sd = {k: v for k, v in sd.items() if "word_embeddings" not in k}
     own = model.state_dict()
     unexpected = sorted(set(sd) - set(own))
     missing = sorted(k for k in set(own) - set(sd) if "word_embeddings" not in k)  # never read (inputs_embeds path)

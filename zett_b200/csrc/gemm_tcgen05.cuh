@@ -154,7 +154,9 @@ __device__ __forceinline__ void epilogue_quads(const EpilogueParams& ep, uint32_
     rd += 16u * 128u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (16 * half + 4 * i < n_rows) {
+      // (arithmetic is unconditional, only the memory accesses are guarded: straight-line code the scheduler can interleave)
+      const bool live = 16 * half + 4 * i < n_rows;
+      {
         float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
         if (scaled) {
           v[0] = fmaf(v[0], q.ws.x, q.b.x); v[1] = fmaf(v[1], q.ws.y, q.b.y);
@@ -168,25 +170,29 @@ __device__ __forceinline__ void epilogue_quads(const EpilogueParams& ep, uint32_
           for (int j = 0; j < 4; ++j) v[j] = gelu_erf_f(v[j]);
         }
         if (pr) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(pr));
+          const float4 t = live ? __ldg(reinterpret_cast<const float4*>(pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
           v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
         }
         if (affine) {  // Rescaler: w * y + b with two roundings, as torch evaluates it (modeling_hypernet.py:18-19)
           v[0] = __fadd_rn(__fmul_rn(q.cs.x, v[0]), q.ct.x); v[1] = __fadd_rn(__fmul_rn(q.cs.y, v[1]), q.ct.y);
           v[2] = __fadd_rn(__fmul_rn(q.cs.z, v[2]), q.ct.z); v[3] = __fadd_rn(__fmul_rn(q.cs.w, v[3]), q.ct.w);
         }
-        if (F32) {
+        if (F32 && live) {
           const float4 y = make_float4(v[0], v[1], v[2], v[3]);
           if (ep.stream_f32) __stcs(reinterpret_cast<float4*>(po), y); else *reinterpret_cast<float4*>(po) = y;
         }
         if (OP) {
-          const Packed4 p = pack_operand4(v, fmt, false, bad);
-          *reinterpret_cast<uint2*>(pl + 2 * e) = p.m;
-          if (fmt == kFmtF16F8) {
-            *reinterpret_cast<uint32_t*>(pl + 64 + e) = p.s.x;
-            *reinterpret_cast<uint32_t*>(pl + 96 + e) = p.t;
-          } else if (fmt == kFmtBf16x3) {
-            *reinterpret_cast<uint2*>(pl + 64 + 2 * e) = p.s;
+          uint32_t bad_i = 0;
+          const Packed4 p = pack_operand4(v, fmt, false, bad_i);
+          if (live) {
+            bad |= bad_i;
+            *reinterpret_cast<uint2*>(pl + 2 * e) = p.m;
+            if (fmt == kFmtF16F8) {
+              *reinterpret_cast<uint32_t*>(pl + 64 + e) = p.s.x;
+              *reinterpret_cast<uint32_t*>(pl + 96 + e) = p.t;
+            } else if (fmt == kFmtBf16x3) {
+              *reinterpret_cast<uint2*>(pl + 64 + 2 * e) = p.s;
+            }
           }
         }
       }
@@ -409,7 +415,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(acc), 0);   // the leader's barrier
+      if (lane == 0) mbar_arrive_cluster_relaxed(tmem_empty_bar(acc), 0);   // the leader's barrier
       if (prof) { waited += t1 - t0; busy += clock64() - t1; }
     }
     report_saturation(ep.out_op.sat, bad);

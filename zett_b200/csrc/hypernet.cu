@@ -488,6 +488,8 @@ struct zett_hn {
   zett_hn_stats stats{};
   double coef_t1 = 0, coef_t2 = 0, coef_rows = 0, coef_u = 0, coef_p = 0;  // FLOPs per surface position / encoder position / row / distinct id / distinct pair
   bool dedup_pairs = true;     // first encoder layer: LayerNorm + query/key/value once per distinct (id, position) pair
+  bool stats_fresh = true;     // the next forward starts a new statistics window (set by zett_hn_check)
+  long long pending_passes = 0;  // passes enqueued since the last check (their counts are still on the device)
   bool dedup_ids = true;       // input projection once per distinct id (ZETT_DEDUP_IDS=0 switches both de-duplications off)
   bool auto_terms = true;      // split_terms was left at 0: the caller accepts a fallback to the bf16 split
   std::vector<LinearW*> linears() {
@@ -1171,19 +1173,22 @@ int zett_hn_forward(zett_hn* h, const int32_t* surface_forms_dev, int64_t n_rows
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const long long per_pass = h->cfg.max_rows_per_pass;
   ZETT_TRY(ensure_workspace(h, std::min<long long>(std::max<int64_t>(n_rows, 1), per_pass)));
-  h->gemm.launches = 0;
-  h->gemm.events_used = 0;
-  h->stats = zett_hn_stats{};
-  h->stats.rows = n_rows;
-  const long long first_pass = h->passes;
+  if (h->stats_fresh) {   // statistics cover every forward between two zett_hn_check calls
+    h->gemm.launches = 0;
+    h->gemm.events_used = 0;
+    h->stats = zett_hn_stats{};
+    h->pending_passes = 0;
+    h->stats_fresh = false;
+  }
+  h->stats.rows += n_rows;
   for (long long r0 = 0; r0 < n_rows; r0 += per_pass) {
     const int rows = static_cast<int>(std::min<long long>(per_pass, n_rows - r0));
     ZETT_TRY(forward_pass(h, surface_forms_dev + r0 * h->L, rows, source_emb_dev, v0_rows, lang_index,
                           pred_in_dev + r0 * ld_pred, separate ? pred_out_dev + r0 * ld_pred : nullptr,
                           pred_bias_dev + r0 * ld_bias, ld_pred, ld_bias, stream));
+    ++h->pending_passes;
   }
   h->stats.kernel_launches = h->gemm.launches;
-  h->stats.packed_positions = -(h->passes - first_pass);  // negative = number of passes whose counts are still on the device
   return ZETT_OK;
 }
 
@@ -1198,8 +1203,10 @@ int zett_hn_check(zett_hn* h, void* cuda_stream) {
     h->stats.gemm_ms = h->gemm.collect_ms(&n);
     h->stats.gemm_launches = n;
   }
-  if (h->stats.packed_positions < 0 && h->ws.counts_all) {
-    const long long n_pass = std::min<long long>(-h->stats.packed_positions, kMaxPassSlots);
+  h->stats_fresh = true;
+  if (h->pending_passes > 0 && h->ws.counts_all) {
+    const long long n_pass = std::min<long long>(h->pending_passes, kMaxPassSlots);
+    h->pending_passes = 0;
     std::vector<int> host(static_cast<size_t>(kMaxPassSlots) * kCntSlots);
     ZETT_CUDA(cudaMemcpy(host.data(), h->ws.counts_all, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
     long long t1 = 0, t2 = 0, rows = 0, uq = 0, pq = 0;

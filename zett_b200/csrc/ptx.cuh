@@ -73,6 +73,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
+// the same without release semantics: the arrival orders nothing but the barrier itself.  For "this accumulator has been
+// read" the tcgen05.ld results are already in registers (tcgen05.wait::ld + fence::before_thread_sync); a RELEASE at cluster
+// scope would additionally wait until every global store the warp has issued is visible cluster-wide -- thousands of
+// cycles of epilogue time per tile for an ordering nobody consumes.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

@@ -201,11 +201,27 @@ def transfer_model(hypernet, base_model, base_tokenizer, target_tokenizer, hn_to
     overwrite_special_rows(pred_in, pred_out, pred_bias, source_in.cpu().numpy(),
                            None if source_out is None else source_out.cpu().numpy(), base_tokenizer.all_special_ids, new_ids)
     model = splice_into_model(base_model, pred_in, pred_out, pred_bias)
+    has_bias_param = output_bias_of(model) is not None
     if output is not None:
+        import os
+        os.makedirs(output, exist_ok=True)
         base_tokenizer.save_pretrained(output)   # tokenizer_config.json and other metadata (transfer.py:281-283)
         target_tokenizer.save_pretrained(output)
         model.save_pretrained(output)
-    return model, dict(n_truncated=n_truncated, rows=len(sfm))
+        if not has_bias_param and pred_bias is not None:
+            # the base model has no output-bias parameter (BIAS_PATHS has no entry): the predicted bias is kept next to
+            # the model in Flax's msgpack encoding, as the reference does (scripts/transfer.py:305-310)
+            from .checkpoint import msgpack_serialize
+            with open(os.path.join(output, "bias.msgpack"), "wb") as f:
+                f.write(msgpack_serialize(np.asarray(pred_bias, dtype=np.float32)))
+    return model, dict(n_truncated=n_truncated, rows=len(sfm), bias_written_to="model" if has_bias_param else "bias.msgpack")
+
+
+def output_bias_of(model):
+    """The output-embedding bias parameter of a PyTorch causal LM, or None (the reference's BIAS_PATHS,
+    zett/model/__init__.py:35-41, lists the architectures that have one)."""
+    out_layer = model.get_output_embeddings() if hasattr(model, "get_output_embeddings") else None
+    return None if out_layer is None else getattr(out_layer, "bias", None)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
