@@ -347,8 +347,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 // WARP = false: one block per row (H up to 4 * VEC * blockDim), block-wide reductions.
 // WARP = true : one warp per row (H up to 128 * VEC), shuffle reductions only -- rows of a few KB (H <= 2048) are
 //               latency-bound on the two block barriers otherwise (43 % of the HBM roofline at H = 768).
+// (minimum blocks per SM: without it ptxas hoists every gamma / beta / table load of the unrolled store loop to the top --
+// 196 registers, ONE resident block per SM, 13 % of the HBM rate; four blocks of <= 64 registers have no spills.  The
+// 16-float4-per-lane warp variant keeps its row in 64 registers and gets two.)
 template <bool WARP, int VEC>
-__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+__global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : 4) layernorm_kernel(const LnParams p) {
   __shared__ float red[32];
   const int n = p.n_dev ? *p.n_dev : p.n_host;
   const int H4 = p.H >> 2;
