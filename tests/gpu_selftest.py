@@ -152,7 +152,7 @@ def run_gemm(impl: int):
     return ok
 
 
-def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2)):
+def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2, "res")):
     """Timing probes of the GEMM engine (no parity claim): ms per launch over shapes x formats x tile shapes, with the
     per-role stall picture of one launch when ZETT_GEMM_PROF=1."""
     lib = _lib.load()
@@ -169,7 +169,15 @@ def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2
             for terms in terms_list:
                 for act in acts:
                     iters = 4
-                    ms, rep = _gemm_ex(lib, a, w, b, None, None, None, out, None, act, impl, terms, iters=iters, report=True)
+                    res = None
+                    if act == "res":   # fp32 output + residual (attention-output / MLP-down epilogue)
+                        res, act = torch.randn(m, n, device=dev), 0
+                        label = "res"
+                    else:
+                        label = act
+                    ms, rep = _gemm_ex(lib, a, w, b, res, None, None, out, None, act, impl, terms, iters=iters, report=True)
+                    act = label
+                    del res
                     t = ms / iters
                     print(json.dumps(dict(kind="sweep", m=m, n=n, k=k, impl=impl, terms=terms, act=act, ms=round(t, 4),
                                           tflops=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), prof=rep)), flush=True)

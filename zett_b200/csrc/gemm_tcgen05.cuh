@@ -128,20 +128,54 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
 // GEMM produces (fp32 and / or operand lines) and its activation are template parameters, row pointers advance by
 // constants, and the loop is rolled in two halves of four quads (fully unrolled with both GELUs inlined the epilogue was
 // ~60 KB of SASS per activation -- instruction-cache misses on top).
-template <int ACT, bool F32, bool OP>
+// FLAGS: what the GEMM's epilogue does, as compile-time bits (kEpiGeneric = decide at run time, the catch-all)
+enum : int { kEpiF32 = 1, kEpiOp = 2, kEpiRes = 4, kEpiAffine = 8, kEpiGeneric = 16 };
+
+// The residual of a chunk as one lane sees it: the quads (row 4 i + lane / 8, 4 columns), i = 0..7, fetched ONE CHUNK AHEAD
+// (load_residual): a residual row was written by a LayerNorm kernel hundreds of megabytes ago, so each of these loads is a
+// DRAM round trip, and issued inside the quad loop their latency was exposed eight times per tile -- longer than the whole
+// main loop of a K = 768 tile.
+struct ResidualRegs {
+  float4 r[8];
+};
+
+__device__ __forceinline__ void load_residual(const EpilogueParams& ep, long long row0, int M, int col, int n, int lane, ResidualRegs& rr) {
+  const long long row = row0 + (lane >> 3);
+  const float* pr = ep.residual + row * ep.ld_res + col;
+  const int n_rows = static_cast<int>(min(static_cast<long long>(32), static_cast<long long>(M) - row));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    rr.r[i] = (col < n && 4 * i < n_rows) ? __ldg(reinterpret_cast<const float4*>(pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pr += 4 * ep.ld_res;
+  }
+}
+
+// pull the residual lines of a whole tile share (32 rows x `cols` columns from col0) towards L2 before they are needed
+__device__ __forceinline__ void prefetch_residual_l2(const EpilogueParams& ep, long long row0, int M, int col0, int cols, int n, int lane) {
+  const long long row = row0 + lane;   // one row per lane, one prefetch per 128-byte line
+  if (row >= M) return;
+  const float* pr = ep.residual + row * ep.ld_res;
+  for (int c = col0; c < col0 + cols && c < n; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + c));
+}
+
+template <int FMT, int ACT, int FLAGS>
 __device__ __forceinline__ void epilogue_quads(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col,
-                                               const QuadConsts& q, uint32_t& bad) {
+                                               const QuadConsts& q, const ResidualRegs& rres, uint32_t& bad) {
+  constexpr bool generic = (FLAGS & kEpiGeneric) != 0;
+  const bool f32 = generic ? ep.out_f32 != nullptr : (FLAGS & kEpiF32) != 0;
+  const bool op = generic ? ep.out_op.base != nullptr : (FLAGS & kEpiOp) != 0;
+  const bool res = generic ? ep.residual != nullptr : (FLAGS & kEpiRes) != 0;
+  const bool affine = generic ? ep.col_scale != nullptr : (FLAGS & kEpiAffine) != 0;
+  const bool scaled = generic ? (ep.w_scale != nullptr || ep.bias != nullptr) : true;   // (identity constants otherwise)
   const int jj = lane & 7, rsub = lane >> 3;
   const long long row = row0 + rsub;                    // this lane's rows are row, row + 4, ..., row + 28
   const int n_rows = static_cast<int>(min(static_cast<long long>(32), static_cast<long long>(M) - row));   // valid while 4 i < n_rows
-  float* po = F32 ? ep.out_f32 + row * ep.ld_out + col : nullptr;
-  const float* pr = ep.residual ? ep.residual + row * ep.ld_res + col : nullptr;
-  int e = 0;
-  uint8_t* pl = nullptr;
-  if (OP) pl = operand_line(ep.out_op, row, col, e);
-  const bool scaled = ep.w_scale != nullptr || ep.bias != nullptr;
-  const bool affine = ep.col_scale != nullptr;
-  const int fmt = ep.out_op.fmt;
+  float* po = f32 ? ep.out_f32 + row * ep.ld_out + col : nullptr;
+  // operand lines of the output: FMT is the engine's format, the one the next GEMM reads
+  constexpr int kShift = FMT == kFmtBf16x1 ? 6 : 5;
+  const int e = col & ((1 << kShift) - 1);
+  uint8_t* pl = op ? ep.out_op.base + row * ep.out_op.ld_bytes + static_cast<long long>(col >> kShift) * 128 : nullptr;
+  const long long so = 4 * ep.ld_out, sl = 4 * ep.out_op.ld_bytes;
   uint32_t rd = stg + static_cast<uint32_t>(rsub) * 128u;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
@@ -156,61 +190,77 @@ __device__ __forceinline__ void epilogue_quads(const EpilogueParams& ep, uint32_
     for (int i = 0; i < 4; ++i) {
       // (arithmetic is unconditional, only the memory accesses are guarded: straight-line code the scheduler can interleave)
       const bool live = 16 * half + 4 * i < n_rows;
-      {
-        float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
-        if (scaled) {
-          v[0] = fmaf(v[0], q.ws.x, q.b.x); v[1] = fmaf(v[1], q.ws.y, q.b.y);
-          v[2] = fmaf(v[2], q.ws.z, q.b.z); v[3] = fmaf(v[3], q.ws.w, q.b.w);
-        }
-        if (ACT == kActGeluTanh) {
+      float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+      if (scaled) {
+        v[0] = fmaf(v[0], q.ws.x, q.b.x); v[1] = fmaf(v[1], q.ws.y, q.b.y);
+        v[2] = fmaf(v[2], q.ws.z, q.b.z); v[3] = fmaf(v[3], q.ws.w, q.b.w);
+      }
+      if (ACT == kActGeluTanh) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_f(v[j]);
-        } else if (ACT == kActGeluErf) {
+        for (int j = 0; j < 4; ++j) v[j] = gelu_tanh_f(v[j]);
+      } else if (ACT == kActGeluErf) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = gelu_erf_f(v[j]);
-        }
-        if (pr) {
-          const float4 t = live ? __ldg(reinterpret_cast<const float4*>(pr)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-        }
-        if (affine) {  // Rescaler: w * y + b with two roundings, as torch evaluates it (modeling_hypernet.py:18-19)
-          v[0] = __fadd_rn(__fmul_rn(q.cs.x, v[0]), q.ct.x); v[1] = __fadd_rn(__fmul_rn(q.cs.y, v[1]), q.ct.y);
-          v[2] = __fadd_rn(__fmul_rn(q.cs.z, v[2]), q.ct.z); v[3] = __fadd_rn(__fmul_rn(q.cs.w, v[3]), q.ct.w);
-        }
-        if (F32 && live) {
+        for (int j = 0; j < 4; ++j) v[j] = gelu_erf_f(v[j]);
+      }
+      if (res) {
+        const float4 t = half == 0 ? rres.r[i] : rres.r[4 + i];
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+      }
+      if (affine) {  // Rescaler: w * y + b with two roundings, as torch evaluates it (modeling_hypernet.py:18-19)
+        v[0] = __fadd_rn(__fmul_rn(q.cs.x, v[0]), q.ct.x); v[1] = __fadd_rn(__fmul_rn(q.cs.y, v[1]), q.ct.y);
+        v[2] = __fadd_rn(__fmul_rn(q.cs.z, v[2]), q.ct.z); v[3] = __fadd_rn(__fmul_rn(q.cs.w, v[3]), q.ct.w);
+      }
+      if (f32) {
+        if (live) {
           const float4 y = make_float4(v[0], v[1], v[2], v[3]);
           if (ep.stream_f32) __stcs(reinterpret_cast<float4*>(po), y); else *reinterpret_cast<float4*>(po) = y;
         }
-        if (OP) {
-          uint32_t bad_i = 0;
-          const Packed4 p = pack_operand4(v, fmt, false, bad_i);
-          if (live) {
-            bad |= bad_i;
-            *reinterpret_cast<uint2*>(pl + 2 * e) = p.m;
-            if (fmt == kFmtF16F8) {
-              *reinterpret_cast<uint32_t*>(pl + 64 + e) = p.s.x;
-              *reinterpret_cast<uint32_t*>(pl + 96 + e) = p.t;
-            } else if (fmt == kFmtBf16x3) {
-              *reinterpret_cast<uint2*>(pl + 64 + 2 * e) = p.s;
-            }
+        po += so;
+      }
+      if (op) {
+        uint32_t bad_i = 0;
+        const Packed4 p = pack_operand4(v, FMT, false, bad_i);
+        if (live) {
+          bad |= bad_i;
+          *reinterpret_cast<uint2*>(pl + 2 * e) = p.m;
+          if (FMT == kFmtF16F8) {
+            *reinterpret_cast<uint32_t*>(pl + 64 + e) = p.s.x;
+            *reinterpret_cast<uint32_t*>(pl + 96 + e) = p.t;
+          } else if (FMT == kFmtBf16x3) {
+            *reinterpret_cast<uint2*>(pl + 64 + 2 * e) = p.s;
           }
         }
+        pl += sl;
       }
-      if (F32) po += 4 * ep.ld_out;
-      if (pr) pr += 4 * ep.ld_res;
-      if (OP) pl += 4 * ep.out_op.ld_bytes;
     }
   }
 }
 
-template <int ACT>
-__device__ __forceinline__ void epilogue_quads_mode(const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M, int col,
-                                                    const QuadConsts& q, uint32_t& bad) {
-  const bool f32 = ep.out_f32 != nullptr, op = ep.out_op.base != nullptr;
-  if (f32 && !op) epilogue_quads<ACT, true, false>(ep, stg, lane, row0, M, col, q, bad);
-  else if (!f32 && op) epilogue_quads<ACT, false, true>(ep, stg, lane, row0, M, col, q, bad);
-  else if (f32 && op) epilogue_quads<ACT, true, true>(ep, stg, lane, row0, M, col, q, bad);
-  else epilogue_quads<ACT, false, false>(ep, stg, lane, row0, M, col, q, bad);   // timing probe: arithmetic, no stores
+// The epilogues the hypernetwork forward actually issues get straight-line instantiations; anything else (the unit tests'
+// combinations) takes the run-time-flag version.  `code` = activation * 16 + flags, uniform over the launch.
+template <int FMT>
+__device__ __forceinline__ void epilogue_dispatch(int code, const EpilogueParams& ep, uint32_t stg, int lane, long long row0, int M,
+                                                  int col, const QuadConsts& q, const ResidualRegs& rres, uint32_t& bad) {
+  switch (code) {
+    case kActNone * 16 + kEpiF32:                          // QKV, last-layer K/V and Q
+      epilogue_quads<FMT, kActNone, kEpiF32>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    case kActNone * 16 + (kEpiF32 | kEpiRes):              // attention output and MLP down projections (+ residual)
+      epilogue_quads<FMT, kActNone, kEpiF32 | kEpiRes>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    case kActGeluErf * 16 + kEpiOp:                        // encoder MLP up projection
+      epilogue_quads<FMT, kActGeluErf, kEpiOp>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    case kActGeluTanh * 16 + kEpiOp:                       // ProjectorBlock dense1
+      epilogue_quads<FMT, kActGeluTanh, kEpiOp>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    case kActGeluTanh * 16 + (kEpiF32 | kEpiRes):          // ProjectorBlock dense2 (+ residual)
+      epilogue_quads<FMT, kActGeluTanh, kEpiF32 | kEpiRes>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    case kActNone * 16 + (kEpiF32 | kEpiOp):               // input projection Linear
+      epilogue_quads<FMT, kActNone, kEpiF32 | kEpiOp>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    case kActNone * 16 + (kEpiF32 | kEpiAffine):           // output heads with the Rescaler
+      epilogue_quads<FMT, kActNone, kEpiF32 | kEpiAffine>(ep, stg, lane, row0, M, col, q, rres, bad); break;
+    default:
+      if (ep.act == kActGeluErf) epilogue_quads<FMT, kActGeluErf, kEpiGeneric>(ep, stg, lane, row0, M, col, q, rres, bad);
+      else if (ep.act == kActGeluTanh) epilogue_quads<FMT, kActGeluTanh, kEpiGeneric>(ep, stg, lane, row0, M, col, q, rres, bad);
+      else epilogue_quads<FMT, kActNone, kEpiGeneric>(ep, stg, lane, row0, M, col, q, rres, bad);
+  }
 }
 
 // tmap_a: box {128 B, 128 rows} over A's lines;  tmap_b: box {128 B, HALVES * block_n / 2 rows} over W's lines
@@ -357,6 +407,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t bad = 0;
     long long waited = 0, busy = 0, t_ldwait = 0, t_stage = 0, t_quads = 0;
     int iter = 0;
+    // a straight-line instantiation exists only for epilogues with a bias / weight scale (every Linear of the forward)
+    const int epi_flags = (ep.out_f32 ? kEpiF32 : 0) | (ep.out_op.base ? kEpiOp : 0) | (ep.residual ? kEpiRes : 0) | (ep.col_scale ? kEpiAffine : 0);
+    const int epi_code = (ep.bias != nullptr || ep.w_scale != nullptr) ? ep.act * 16 + epi_flags : -1;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
       const long long row0 = static_cast<long long>(tc.m_blk) * tile_m + static_cast<int>(cta_rank) * kBlockM + quarter * 32;
@@ -367,14 +420,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t acc_phase = HALVES == 2 ? (iter & 1u) : ((iter >> 1) & 1u);
       const int c_first = HALVES == 2 ? 0 : 32 * group;
       const int c_step = HALVES == 2 ? 32 : 64;
-      const long long t0 = prof ? clock64() : 0;
-      mbar_wait(tmem_full_bar(acc), acc_phase, 4);
-      const long long t1 = prof ? clock64() : 0;
-      tc_fence_after();
       // accumulator column c holds W row (c < load_n ? CTA 0's : CTA 1's) share of this half:
       //   output column = tile origin + (c / load_n) * load_n * HALVES + hf * load_n + c % load_n   (= origin + c when HALVES == 1)
       const int col_tile = tc.n_blk * tile_n + hf * load_n;
       auto gcol = [&](int c) { return col_tile + (c < load_n ? c : c + load_n * (HALVES - 1)); };
+      // the residual does not depend on the accumulator: start pulling it in while the MMAs of this tile are still running
+      ResidualRegs rres;
+      const bool has_res = ep.residual != nullptr;
+      if (has_res) {
+        for (int c = c_first; c < s.block_n; c += c_step) prefetch_residual_l2(ep, row0, M, gcol(c), 32, s.n, lane);
+        if (c_first < s.block_n) load_residual(ep, row0, M, gcol(c_first) + 4 * (lane & 7), s.n, lane, rres);
+      }
+      const long long t0 = prof ? clock64() : 0;
+      mbar_wait(tmem_full_bar(acc), acc_phase, 4);
+      const long long t1 = prof ? clock64() : 0;
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * s.block_n);
       // one register chunk: its rows go to the staging tile, then the tcgen05.ld of the NEXT chunk is issued into the same
       // registers and lands while this chunk's quads are processed out of shared memory
@@ -405,11 +465,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __syncwarp();
         const long long p2 = prof ? clock64() : 0;
-        if (col < s.n) {
-          if (ep.act == kActGeluErf) epilogue_quads_mode<kActGeluErf>(ep, stg, lane, row0, M, col, q, bad);
-          else if (ep.act == kActGeluTanh) epilogue_quads_mode<kActGeluTanh>(ep, stg, lane, row0, M, col, q, bad);
-          else epilogue_quads_mode<kActNone>(ep, stg, lane, row0, M, col, q, bad);
-        }
+        if (col < s.n) epilogue_dispatch<FMT>(epi_code, ep, stg, lane, row0, M, col, q, rres, bad);
+        if (has_res && c + c_step < s.block_n) load_residual(ep, row0, M, col_next, s.n, lane, rres);   // for the next chunk
         __syncwarp();  // the staging tile is rewritten by the next chunk
         if (prof) { t_ldwait += p1 - p0; t_stage += p2 - p1; t_quads += clock64() - p2; }
       }
