@@ -25,14 +25,28 @@ struct EpilogueParams {
   int stream_f32;           // 1: fp32 output stored with the streaming (evict-first) hint
 };
 
-// F.gelu(x, approximate="tanh")  (ProjectorBlock, hf_hypernet/modeling_hypernet.py:36-39)
+// F.gelu(x, approximate="tanh")  (ProjectorBlock, hf_hypernet/modeling_hypernet.py:36-39):
+//     0.5 x (1 + tanh(u)) = x / (1 + exp(-2 u)),  u = sqrt(2/pi) (x + 0.044715 x^3)
+// one MUFU.EX2 and one MUFU.RCP instead of tanhf's branchy ~25 instructions; relative error ~2e-7.  (The epilogue warps
+// share the SM's four issue ports with nothing else, and at K = 768 a tile's main loop is only ~12 000 cycles.)
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float c = 0.7978845608028654f;  // sqrt(2/pi)
-  return 0.5f * x * (1.0f + tanhf(c * (x + 0.044715f * x * x * x)));
+  const float c2 = -2.0f * 0.7978845608028654f;  // -2 sqrt(2/pi)
+  const float u2 = c2 * fmaf(0.044715f * x * x, x, x);
+  return x * __frcp_rn(1.0f + __expf(u2));
 }
-// exact GELU, hidden_act="gelu" of the RoBERTa encoder
+// exact GELU, hidden_act="gelu" of the RoBERTa encoder: 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 ABSOLUTE, which is what matters next to the 1; branch-free: erff's two ranges diverge inside a warp)
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+  const float z = x * 0.7071067811865476f;
+  const float az = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * __expf(-az * az);            // 1 - erf(|z|)
+  const float one_plus_erf = z >= 0.f ? 2.0f - e : e;  // 1 + erf(z)
+  return 0.5f * x * one_plus_erf;
 }
 
 // per-column constants of a quad (loaded once per lane and accumulator chunk: the lane's columns do not change with the row)
