@@ -152,7 +152,7 @@ def run_gemm(impl: int):
     return ok
 
 
-def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2, "res")):
+def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2, "res", "erf_op", "tanh_op")):
     """Timing probes of the GEMM engine (no parity claim): ms per launch over shapes x formats x tile shapes, with the
     per-role stall picture of one launch when ZETT_GEMM_PROF=1."""
     lib = _lib.load()
@@ -169,13 +169,12 @@ def run_sweep(shapes=None, impls=(2, 5), terms_list=(2, 3, 1), acts=(0, 0x100, 2
             for terms in terms_list:
                 for act in acts:
                     iters = 4
-                    res = None
+                    res, o32, oop, label = None, out, None, act
                     if act == "res":   # fp32 output + residual (attention-output / MLP-down epilogue)
                         res, act = torch.randn(m, n, device=dev), 0
-                        label = "res"
-                    else:
-                        label = act
-                    ms, rep = _gemm_ex(lib, a, w, b, res, None, None, out, None, act, impl, terms, iters=iters, report=True)
+                    elif act in ("erf_op", "tanh_op"):   # GELU + operand-line output only (MLP-up / ProjectorBlock dense1 epilogue)
+                        o32, oop, act = None, out, (2 if act == "erf_op" else 1)
+                    ms, rep = _gemm_ex(lib, a, w, b, res, None, None, o32, oop, act, impl, terms, iters=iters, report=True)
                     act = label
                     del res
                     t = ms / iters

@@ -29,17 +29,23 @@ struct EpilogueParams {
 //     0.5 x (1 + tanh(u)) = x / (1 + exp(-2 u)),  u = sqrt(2/pi) (x + 0.044715 x^3)
 // one MUFU.EX2 and one MUFU.RCP instead of tanhf's branchy ~25 instructions; relative error ~2e-7.  (The epilogue warps
 // share the SM's four issue ports with nothing else, and at K = 768 a tile's main loop is only ~12 000 cycles.)
+// (rcp.approx / ex2.approx: one MUFU each, ~1 ulp; __frcp_rn is the IEEE-rounded sequence and cost more than tanhf did)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float c2 = -2.0f * 0.7978845608028654f;  // -2 sqrt(2/pi)
   const float u2 = c2 * fmaf(0.044715f * x * x, x, x);
-  return x * __frcp_rn(1.0f + __expf(u2));
+  return x * rcp_approx(1.0f + __expf(u2));
 }
 // exact GELU, hidden_act="gelu" of the RoBERTa encoder: 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz & Stegun 7.1.26
 // (|error| <= 1.5e-7 ABSOLUTE, which is what matters next to the 1; branch-free: erff's two ranges diverge inside a warp)
 __device__ __forceinline__ float gelu_erf_f(float x) {
   const float z = x * 0.7071067811865476f;
   const float az = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, az, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

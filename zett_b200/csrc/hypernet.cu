@@ -490,7 +490,6 @@ struct zett_hn {
   bool dedup_pairs = true;     // first encoder layer: LayerNorm + query/key/value once per distinct (id, position) pair
   bool stats_fresh = true;     // the next forward starts a new statistics window (set by zett_hn_check)
   long long pending_passes = 0;  // passes enqueued since the last check (their counts are still on the device)
-  bool attn_streaming = false; // ZETT_ATTN_STREAMING=1: the looped attention kernel even for rows of <= 8 positions (A/B probe)
   bool dedup_ids = true;       // input projection once per distinct id (ZETT_DEDUP_IDS=0 switches both de-duplications off)
   bool auto_terms = true;      // split_terms was left at 0: the caller accepts a fallback to the bf16 split
   std::vector<LinearW*> linears() {
@@ -709,20 +708,10 @@ int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
   const long long warps = static_cast<long long>(p.n_rows) * ((p.n_heads + hpw - 1) / hpw);
   if (warps == 0) return ZETT_OK;
   const int grid = static_cast<int>((warps + 7) / 8);
-  const bool rows_in_registers = h->S <= 8 && !h->attn_streaming;   // every shipped configuration
   switch (h->dh) {
-    case 32:
-      if (rows_in_registers) attention_rows_kernel<8, 1, 8><<<grid, 256, 0, stream>>>(p);
-      else attention_kernel<8, 1><<<grid, 256, 0, stream>>>(p);
-      break;
-    case 64:
-      if (rows_in_registers) attention_rows_kernel<16, 1, 8><<<grid, 256, 0, stream>>>(p);
-      else attention_kernel<16, 1><<<grid, 256, 0, stream>>>(p);
-      break;
-    case 128:
-      if (rows_in_registers) attention_rows_kernel<32, 1, 8><<<grid, 256, 0, stream>>>(p);
-      else attention_kernel<32, 1><<<grid, 256, 0, stream>>>(p);
-      break;
+    case 32: attention_kernel<8, 1><<<grid, 256, 0, stream>>>(p); break;
+    case 64: attention_kernel<16, 1><<<grid, 256, 0, stream>>>(p); break;
+    case 128: attention_kernel<32, 1><<<grid, 256, 0, stream>>>(p); break;
     case 256: attention_kernel<32, 2><<<grid, 256, 0, stream>>>(p); break;
     default: return fail(ZETT_ERR_UNSUPPORTED, "attention head size must be 32, 64, 128 or 256");
   }
@@ -1046,7 +1035,6 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   h->gemm.read_env();
   if (const char* e = getenv("ZETT_DEDUP_PAIRS")) h->dedup_pairs = atoi(e) != 0;
   if (const char* e = getenv("ZETT_DEDUP_IDS")) h->dedup_ids = atoi(e) != 0;
-  if (const char* e = getenv("ZETT_ATTN_STREAMING")) h->attn_streaming = atoi(e) != 0;
   if (!h->dedup_ids) h->dedup_pairs = false;   // the pair table is built on the distinct-id numbering
   if (cudaMalloc(&h->flags, sizeof(unsigned int) * kFlagSlots) != cudaSuccess || cudaMemset(h->flags, 0, sizeof(unsigned int) * kFlagSlots) != cudaSuccess) {
     delete h;

@@ -477,7 +477,9 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   const bool any_valid = valid_mask != 0;
   const int n_q = p.row0_only ? 1 : n;
   uint32_t bad = 0;
-  // K and V are streamed per query (L1-resident re-reads); keeping them in registers was measured slower
+  // K and V are streamed per query (L1-resident re-reads).  Keeping a row's keys and values in registers (all loads issued
+  // up front, 128 registers, two resident blocks per SM) was measured slower twice: round 1, and again in round 2 as a
+  // separate kernel -- 15.4 vs 14.5 ms per XLM-R-shape step.
   for (int i = 0; i < n_q; ++i) {
     const long long qi = p.row0_only ? r : (p.qkv_index ? __ldg(p.qkv_index + t0 + i) : (t0 + i));
     float4 qv[VPL];
@@ -522,102 +524,6 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
       for (int d = 0; d < VPL; ++d) {
         const float y[4] = {acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv};
         store_operand4(p.out, orow, hoff + 4 * LPH * d, y, false, bad);
-      }
-    }
-  }
-  report_saturation(p.out.sat, bad);
-}
-
-// The same attention for rows of at most NMAX positions (every shipped configuration: S = 7 or 8), with the row's keys and
-// values held in REGISTERS: all of a row's q / k / v vectors are requested back to back (3 n independent 16-byte loads per
-// lane instead of a dependent load inside a loop per (query, key) pair), the scores of a query are complete before its
-// softmax (max, exp, sum, divide -- the order torch evaluates it in), and keys are never re-read.  Loops are unrolled to
-// NMAX with warp-uniform guards, so a row of n positions executes n^2 dot products, not NMAX^2.
-template <int LPH, int VPL, int NMAX>
-__global__ void __launch_bounds__(256) attention_rows_kernel(const AttnParams p) {
-  constexpr int HPW = 32 / LPH;  // heads per warp
-  const int lane = threadIdx.x & 31;
-  const int groups = (p.n_heads + HPW - 1) / HPW;
-  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wid >= static_cast<long long>(p.n_rows) * groups) return;
-  const int r = static_cast<int>(wid / groups);
-  const int h = static_cast<int>(wid % groups) * HPW + lane / LPH;
-  const bool head_ok = h < p.n_heads;               // lanes of a missing head still take part in the shuffles
-  const int hoff = (head_ok ? h : 0) * p.dh + (lane % LPH) * 4;
-  const int t0 = __ldg(p.row_start + r);
-  const int n = min(NMAX, __ldg(p.row_start + r + 1) - t0);
-  uint32_t valid_mask = 0;
-#pragma unroll
-  for (int j = 0; j < NMAX; ++j)
-    if (j < n) valid_mask |= (__ldg(p.valid + t0 + j) != 0 ? 1u : 0u) << j;
-  const bool any_valid = valid_mask != 0;
-  const uint32_t use_mask = any_valid ? valid_mask : ((1u << n) - 1u);   // no valid key: uniform weights over all positions
-  const int n_q = p.row0_only ? 1 : n;
-  uint32_t bad = 0;
-
-  float4 kr[NMAX][VPL], vr[NMAX][VPL], qr[NMAX][VPL];
-#pragma unroll
-  for (int j = 0; j < NMAX; ++j) {
-    if (j < n) {
-      const long long tj = p.qkv_index ? __ldg(p.qkv_index + t0 + j) : (t0 + j);
-      if ((use_mask >> j) & 1u) {
-#pragma unroll
-        for (int d = 0; d < VPL; ++d) {
-          if (any_valid) kr[j][d] = __ldg(reinterpret_cast<const float4*>(p.k + tj * p.ldk + hoff + 4 * LPH * d));
-          vr[j][d] = __ldg(reinterpret_cast<const float4*>(p.v + tj * p.ldv + hoff + 4 * LPH * d));
-        }
-      }
-      if (j < n_q) {
-        const long long qj = p.row0_only ? r : tj;
-#pragma unroll
-        for (int d = 0; d < VPL; ++d) qr[j][d] = __ldg(reinterpret_cast<const float4*>(p.q + qj * p.ldq + hoff + 4 * LPH * d));
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NMAX; ++i) {
-    if (i < n_q) {
-      float sc[NMAX];
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < NMAX; ++j) {
-        if (j < n && ((use_mask >> j) & 1u)) {
-          float s = 0.f;
-          if (any_valid) {
-#pragma unroll
-            for (int d = 0; d < VPL; ++d)
-              s += (qr[i][d].x * kr[j][d].x + qr[i][d].y * kr[j][d].y) + (qr[i][d].z * kr[j][d].z + qr[i][d].w * kr[j][d].w);
-#pragma unroll
-            for (int o = LPH / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-            s *= p.scale;
-          }
-          sc[j] = s;
-          m = fmaxf(m, s);
-        }
-      }
-      float l = 0.f;
-      float4 acc[VPL];
-#pragma unroll
-      for (int d = 0; d < VPL; ++d) acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < NMAX; ++j) {
-        if (j < n && ((use_mask >> j) & 1u)) {
-          const float w = expf(sc[j] - m);
-          l += w;
-#pragma unroll
-          for (int d = 0; d < VPL; ++d) {
-            acc[d].x += w * vr[j][d].x; acc[d].y += w * vr[j][d].y; acc[d].z += w * vr[j][d].z; acc[d].w += w * vr[j][d].w;
-          }
-        }
-      }
-      const float inv = 1.0f / l;
-      const long long orow = p.row0_only ? r : (t0 + i);
-      if (head_ok) {
-#pragma unroll
-        for (int d = 0; d < VPL; ++d) {
-          const float y[4] = {acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv};
-          store_operand4(p.out, orow, hoff + 4 * LPH * d, y, false, bad);
-        }
       }
     }
   }
