@@ -243,6 +243,32 @@ int zett_surface_forms_blob(const zett_tok* t, const char* tokens_blob, int64_t 
 
 void zett_tok_destroy(zett_tok* t);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * TokenizerSampler (training side; SURVEY section 8f, last row).
+ * Replaces rust_utils.TokenizerSampler.sample_tokenizer          (reference rust_utils/src/lib.rs:69-250),
+ * called by the training collator                                  (reference zett/collator.py:341-452).
+ * Host-side C++: GPT-2 pre-tokenisation (Unicode-aware), byte-level substring scores, the seed cache of the last
+ * batches and the seed list of a Unigram tokenizer.  The reference draws its noise from an unseeded generator and
+ * iterates hash maps; here the noise takes a seed (none is drawn at noise_std = 0), the byte alphabet comes in byte order
+ * and ties in the score order are broken by the piece's bytes.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct zett_sampler zett_sampler;
+
+int zett_sampler_create(zett_sampler** out);
+
+/* texts_blob: n_texts UTF-8 strings back to back, NUL-terminated; counts[n_texts] their frequencies (the reference's
+ * HashMap<String, u32>).  seed_size, max_length, stride, noise_std, pop_prev, push_current as in the reference
+ * (defaults there: stride 1, noise_std 0, pop_prev / push_current true).  On success *out_pieces_blob (out_n strings back to
+ * back, NUL-terminated, *out_blob_bytes long) and *out_scores (out_n log-probabilities) are malloc'd by the callee and
+ * released with zett_sampler_free. */
+int zett_sampler_sample(zett_sampler* s, const char* texts_blob, int64_t blob_bytes, const uint32_t* counts, int64_t n_texts,
+                        int64_t seed_size, int64_t max_length, int64_t stride, double noise_std, uint64_t noise_seed,
+                        int pop_prev, int push_current, char** out_pieces_blob, int64_t* out_blob_bytes, double** out_scores,
+                        int64_t* out_n);
+
+void zett_sampler_free(void* p);
+void zett_sampler_destroy(zett_sampler* s);
+
 #ifdef __cplusplus
 }
 #endif

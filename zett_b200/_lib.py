@@ -16,8 +16,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libzett_b200.so")
-SOURCES = ["hypernet.cu", "retok.cpp", "comm.cpp"]
-HEADERS = ["ptx.cuh", "operand.cuh", "gemm_tcgen05.cuh", "epilogue.cuh", "kernels.cuh"]
+SOURCES = ["hypernet.cu", "retok.cpp", "comm.cpp", "sampler.cpp"]
+HEADERS = ["ptx.cuh", "operand.cuh", "gemm_tcgen05.cuh", "epilogue.cuh", "kernels.cuh", "unicode_tables.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
@@ -110,6 +110,11 @@ SIGNATURES = {
     "zett_surface_forms_blob": (c_int, [c_void_p, c_char_p, c_int64, c_int64, c_char_p, c_int64, POINTER(c_int32), c_int64,
                                         c_int32, c_int32, c_int64, POINTER(c_int32), POINTER(c_int64), c_int]),
     "zett_tok_destroy": (None, [c_void_p]),
+    "zett_sampler_create": (c_int, [POINTER(c_void_p)]),
+    "zett_sampler_sample": (c_int, [c_void_p, c_char_p, c_int64, POINTER(ctypes.c_uint32), c_int64, c_int64, c_int64, c_int64, c_double,
+                                    ctypes.c_uint64, c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_int64)]),
+    "zett_sampler_free": (None, [c_void_p]),
+    "zett_sampler_destroy": (None, [c_void_p]),
 }
 
 
