@@ -339,6 +339,11 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
     plan = parallel.shard_plan(world * rows, world, P)
     full = torch.zeros((plan[-1][0] + world * plan[-1][1], width), dtype=torch.float32, device=dev)
     main_stream = torch.cuda.current_stream(dev)
+    transport = "none"
+    if world > 1:
+        transport = os.environ.get("ZETT_GATHER", "p2p")
+        if transport == "p2p":   # peer copies over NVLink (copy engines) instead of ncclAllGather: the GEMMs keep every SM
+            d.comm.register(full)
 
     def slot_of(base, per, n_here):
         return full[base + rank * per: base + rank * per + n_here]
@@ -358,6 +363,7 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
             loc += n_here
         if world > 1:
             main_stream.wait_stream(d.side)
+            d.comm.barrier(main_stream)
 
     # ---- device-resident throughput ("value") ----------------------------------------------------------------------
     nat.set_timing(True)
@@ -463,6 +469,8 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
         e2e = {"value": world * rows / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(world * rows * cfg.hn_surface_maxlen * 4),
                "d2h_bytes_per_step": int(world * rows * width * 4), "ms_per_step": e2e_s * 1e3}
     nat.close()
+    if world > 1:
+        d.comm.unregister()
     del src, sf_dev, full
     torch.cuda.empty_cache()
 
@@ -475,6 +483,8 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
         "config": {
             "workload": wl["workload"] + ("" if vocab == "random" else " [target vocabulary: concatenations of hn pieces]"),
             "rows_per_gpu": rows, "total_rows": world * rows, "parallelism": "rows x%d" % world,
+            "gather": {"none": "single GPU", "p2p": "zett_allgather_rows: peer copies per super-block on a side stream (copy engines, NVLink)",
+                       "nccl": "zett_allgather_rows: ncclAllGather per super-block on a side stream"}.get(transport, transport),
             "hn_tokenizer": (hn_kind or wl["hn"]) + " 32k synthetic", "nonpad_length_histogram": hist, "truncated": n_trunc,
             "l2": "inputs larger than L2 (weights + per-pass activations are GBs; nothing is re-read from a warm L2 by design)",
             "gemm_impl": int(st["gemm_impl"]), "split_terms": terms, "rows_per_pass": P,

@@ -196,6 +196,19 @@ int zett_comm_init(int rank, int world, const void* nccl_unique_id, zett_comm** 
 int zett_allgather_rows(zett_comm* c, const float* shard_dev, int64_t rows_per_rank, int64_t row_elems, float* full_dev,
                         void* cuda_stream);
 
+/* Peer-copy transport.  A full matrix that every rank holds at the same size can be REGISTERED: each rank describes its
+ * buffer with zett_comm_ipc_handle (a 64-byte CUDA IPC handle + the buffer's offset inside its allocation), the host
+ * application passes everybody's 64-byte handles and offsets to zett_comm_register (collective), and from then on
+ * zett_allgather_rows into that buffer does not launch a kernel: every rank pushes its rows into its slot of every peer's
+ * buffer with asynchronous peer copies on `cuda_stream` (copy engines over NVLink / NVSwitch, no SM).  The pushes of a
+ * rank complete in its own stream order; zett_comm_barrier (a one-element ncclAllReduce on `cuda_stream`) completes when
+ * every rank has reached it, i.e. when everything pushed before it on every rank has landed.  Unregister before freeing
+ * the buffer. */
+int zett_comm_ipc_handle(const void* dev_ptr, void* out_handle_64_bytes, int64_t* out_offset);
+int zett_comm_register(zett_comm* c, void* full_dev, int64_t bytes, const void* all_handles, const int64_t* all_offsets);
+int zett_comm_unregister(zett_comm* c);
+int zett_comm_barrier(zett_comm* c, void* cuda_stream);
+
 /* rank / world of the communicator and the NCCL version in use (0 when world == 1); any pointer may be NULL */
 int zett_comm_info(const zett_comm* c, int* rank, int* world, int* nccl_version);
 

@@ -36,14 +36,22 @@ def main():
         sf, src = torch.from_numpy(sf_np).to(dev), torch.from_numpy(src_np).to(dev)
         single = model(sf, source_embeddings=src, lang_index=None if lang is None else torch.tensor(lang))
         fn = parallel.hypernet_block_fn(model, sf, src, lang)
-        for rpp in (None, 96):
+        for rpp, transport in ((None, "nccl"), (96, "nccl"), (96, "p2p")):
+            full = None
+            if transport == "p2p":   # registered full matrix: the gather becomes peer copies over NVLink
+                full = torch.zeros((parallel.padded_rows(rows, world, rpp), parallel.packed_width(cfg.n_embd, bool(cfg.separate_out_embeddings))),
+                                   dtype=torch.float32, device=dev)
+                comm.register(full)
             sharded = parallel.predict_sharded(rows, cfg.n_embd, bool(cfg.separate_out_embeddings), fn, dev, comm=comm,
-                                               rows_per_pass=rpp)
+                                               rows_per_pass=rpp, full=full)
             torch.cuda.synchronize()
+            if transport == "p2p":
+                sharded = tuple(None if t is None else t.clone() for t in sharded)
+                comm.unregister()
             for a, b in zip(single, sharded):
                 if a is not None and not torch.equal(a, b.contiguous()):
                     ok = False
-                    print(f"rank {rank} {name} rows_per_pass {rpp}: sharded != single, max diff {(a - b).abs().max().item():.3e}", flush=True)
+                    print(f"rank {rank} {name} rows_per_pass {rpp} {transport}: sharded != single, max diff {(a - b).abs().max().item():.3e}", flush=True)
         for a, b in zip(single, sharded):
             if a is None:
                 assert b is None

@@ -99,6 +99,10 @@ SIGNATURES = {
     "zett_comm_unique_id": (c_int, [c_void_p]),
     "zett_comm_init": (c_int, [c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "zett_allgather_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "zett_comm_ipc_handle": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
+    "zett_comm_register": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
+    "zett_comm_unregister": (c_int, [c_void_p]),
+    "zett_comm_barrier": (c_int, [c_void_p, c_void_p]),
     "zett_comm_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "zett_comm_destroy": (None, [c_void_p]),
     "zett_tok_create_unigram": (c_int, [POINTER(c_char_p), POINTER(c_double), c_int64, c_int64, c_int, POINTER(c_void_p)]),

@@ -6,9 +6,11 @@ independent (no cross-row operation in any supported configuration), so the voca
 SUPER-BLOCKS of ``world * rows_per_pass`` consecutive rows, of which rank ``r`` predicts the ``r``-th slice of
 ``rows_per_pass`` rows with its own replica of the weights.  The kernels write ``pred_in | pred_out | bias`` of a row
 side by side straight into this rank's slot of the full ``[rows, n_out * D + 4]`` fp32 matrix (they take the row
-stride), and one in-place all-gather per super-block -- ``zett_allgather_rows`` of libzett_b200.so, i.e. ncclAllGather
-over NVLink / NVSwitch, enqueued on a side stream so that it runs under the next super-block's compute -- fills in the
-other ranks' slots.  Only the last super-block's gather is exposed.  The CPU tests drive the same plan over gloo.
+stride), and one in-place all-gather per super-block -- ``zett_allgather_rows`` of libzett_b200.so, enqueued on a side
+stream so that it runs under the next super-block's compute -- fills in the other ranks' slots.  Its transport is
+ncclAllGather, or, once the full matrix is registered with the communicator (``NativeComm.register``), peer copies over
+NVLink / NVSwitch that need no SM (the persistent GEMMs own all of them).  Only the last super-block's gather is exposed.
+The CPU tests drive the same plan over gloo.
 """
 from __future__ import annotations
 
@@ -102,6 +104,36 @@ class NativeComm:
         self._lib.check(self.lib.zett_allgather_rows(self.handle, ctypes.c_void_p(shard_ptr), per, width,
                                                      ctypes.c_void_p(full_slab.data_ptr()), ctypes.c_void_p(s)))
 
+    def register(self, full: torch.Tensor, group=None):
+        """Collective: from now on ``allgather_rows`` into ``full`` is peer copies (copy engines over NVLink, no kernel) instead
+        of ncclAllGather.  ``full`` must have the same size on every rank.  Handles travel over torch.distributed."""
+        if self.world == 1:
+            return
+        handle, off = ctypes.create_string_buffer(64), ctypes.c_int64(0)
+        self._lib.check(self.lib.zett_comm_ipc_handle(ctypes.c_void_p(full.data_ptr()), handle, ctypes.byref(off)))
+        box = [None] * self.world
+        dist.all_gather_object(box, (handle.raw, int(off.value)), group=group)
+        blob = b"".join(h for h, _ in box)
+        offs = (ctypes.c_int64 * self.world)(*[o for _, o in box])
+        self._lib.check(self.lib.zett_comm_register(self.handle, ctypes.c_void_p(full.data_ptr()), full.numel() * full.element_size(),
+                                                    blob, offs))
+        self._registered = full   # keep the tensor alive while peers map it
+
+    def unregister(self, group=None):
+        if self.world > 1 and getattr(self, "_registered", None) is not None:
+            torch.cuda.synchronize(self._registered.device)
+            dist.barrier(group=group)   # nobody frees its buffer while a peer may still be pushing into it
+            self._lib.check(self.lib.zett_comm_unregister(self.handle))
+            dist.barrier(group=group)
+            self._registered = None
+
+    def barrier(self, stream: Optional[torch.cuda.Stream] = None):
+        """Completes (in stream order) when every rank has reached it: all peer copies enqueued before it have landed."""
+        if self.world == 1:
+            return
+        s = (stream or torch.cuda.current_stream()).cuda_stream
+        self._lib.check(self.lib.zett_comm_barrier(self.handle, ctypes.c_void_p(s)))
+
     def info(self) -> dict:
         r, w, v = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._lib.check(self.lib.zett_comm_info(self.handle, ctypes.byref(r), ctypes.byref(w), ctypes.byref(v)))
@@ -132,6 +164,9 @@ class TorchComm:
             return
         shard = full_slab[self.rank * per:(self.rank + 1) * per].clone()
         dist.all_gather_into_tensor(full_slab, shard, group=self.group)
+
+    def barrier(self, stream=None):
+        """(torch.distributed collectives complete for every rank by themselves)"""
 
 
 def gather_rows(block: torch.Tensor, world: int, group=None) -> torch.Tensor:
@@ -177,6 +212,7 @@ def predict_sharded(n_rows: int, n_embd: int, separate_out: bool, compute_block:
             comm.allgather_rows(slab, per)
     if side is not None:
         torch.cuda.current_stream(device).wait_stream(side)
+    comm.barrier()   # peer copies complete locally: everybody's rows have landed once every rank is past this point
     check = getattr(compute_block, "check", None)
     if check is not None:
         check()  # IndexError for an out-of-range id in ANY pass, as ZettHypernet.forward raises (the kernels clamp and flag)

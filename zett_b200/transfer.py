@@ -313,6 +313,7 @@ class TokenPipeline:
             loc = hi
         if comm is not None and world > 1:
             stream.wait_stream(side)
+            comm.barrier(stream)   # peer copies complete locally; past this point every rank's rows have landed everywhere
         if after_compute is not None:
             after_compute(self.block[:n])
         return self.out_pinned[:n], self.sf_pinned[:n].numpy(), n_trunc
