@@ -51,8 +51,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons of ONE GPU every 200 ms.  It is started before the warm-up steps (nvidia-smi needs
+    about a second to come up on an 8-GPU box, longer than a short timed region) and every sample carries its timestamp, so
+    that `stop` can keep exactly the samples taken while the timed region ran."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -64,12 +66,14 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin / t_end: datetime bounds of the timed region (None = keep every sample)."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -77,22 +81,32 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
+        rows = []
         with open(self.path) as f:
             for line in f:
                 parts = [x.strip() for x in line.split(",")]
-                if len(parts) < 8 or parts[0] != str(self.gpu):
+                if len(parts) < 9 or parts[1] != str(self.gpu):
                     continue
                 try:
-                    sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]), parts[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
         os.unlink(self.path)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t_begin is None or (t_begin <= r[0] <= t_end)]
+        window = "timed region"
+        if not inside and rows:   # region shorter than the sampling period: the samples under load right around it
+            inside = [r for r in rows if r[3] > 0.5 * max(x[3] for x in rows)]
+            window = "warm-up + timed region (no sample fell inside the timed region itself)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "power_w_max": max(r[3] for r in inside) if inside else None, "samples": len(inside), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def build_workload(name, rank, rows, vocab="random", hn_kind=None):
@@ -366,23 +380,26 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
             d.comm.barrier(main_stream)
 
     # ---- device-resident throughput ("value") ----------------------------------------------------------------------
+    import datetime
     nat.set_timing(True)
+    sampler = ClockSampler(d.local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         forward_resident()
     nat.check()
     d.sync_all()
-    sampler = ClockSampler(d.local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d.sync_all()
+    t_begin = datetime.datetime.now()
     e0.record()
     for _ in range(steps):
         forward_resident()
     e1.record()
     d.sync_all()
+    t_end = datetime.datetime.now()
     elapsed_ms = d.max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     nat.check()
     st = nat.stats()  # totals over the `steps` timed steps (the library accumulates between two checks)
     ms_per_step = elapsed_ms / steps
