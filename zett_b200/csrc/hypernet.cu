@@ -683,18 +683,32 @@ int make_projector(zett_hn* h, const std::string& prefix, Projector* p) {
   return ZETT_OK;
 }
 
+template <int FMT>
+void launch_ln_fmt(const LnParams& p, int h4, long long max_rows, cudaStream_t stream) {
+  if (h4 <= 32 * kLnWarpVec) {  // one warp per row, eight rows per block
+    const int grid = static_cast<int>(std::min<long long>((max_rows + 7) / 8, 148LL * 8));
+    if (h4 <= 32 * 4) layernorm_kernel<true, 4, FMT><<<grid, 256, 0, stream>>>(p);
+    else if (h4 <= 32 * 8) layernorm_kernel<true, 8, FMT><<<grid, 256, 0, stream>>>(p);
+    else layernorm_kernel<true, kLnWarpVec, FMT><<<grid, 256, 0, stream>>>(p);
+  } else {
+    // one block per row, eight float4 per thread: 128-thread blocks (eight resident per SM, so eight rows in different
+    // phases of load / reduce / store) up to H = 4096, 256-thread blocks above
+    const int threads = h4 <= 128 * kLnBlockVec ? 128 : 256;
+    const int grid = static_cast<int>(std::min<long long>(max_rows, 148LL * (threads == 128 ? 32 : 16)));
+    layernorm_kernel<false, kLnBlockVec, FMT><<<grid, threads, 0, stream>>>(p);
+  }
+}
+
 int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
   if (max_rows <= 0) return ZETT_OK;
   p.H = h->H;
   const int h4 = h->H / 4;
-  if (h4 <= 32 * kLnWarpVec) {  // one warp per row, eight rows per block
-    const int grid = static_cast<int>(std::min<long long>((max_rows + 7) / 8, 148LL * 8));
-    if (h4 <= 32 * 8) layernorm_kernel<true, 8><<<grid, 256, 0, stream>>>(p);
-    else layernorm_kernel<true, kLnWarpVec><<<grid, 256, 0, stream>>>(p);
-  } else {
-    const int threads = std::min(256, std::max(32, ((h4 + 31) / 32) * 32));
-    const int grid = static_cast<int>(std::min<long long>(max_rows, 148LL * 16));
-    layernorm_kernel<false, kLnMaxVec><<<grid, threads, 0, stream>>>(p);
+  const int fmt = p.out_op.base ? p.out_op.fmt : (p.c_op.base ? p.c_op.fmt : kFmtF16F8);
+  if (p.out_op.base && p.c_op.base && p.out_op.fmt != p.c_op.fmt) return fail(ZETT_ERR_STATE, "layernorm: two operand formats in one launch");
+  switch (fmt) {
+    case kFmtF16F8: launch_ln_fmt<kFmtF16F8>(p, h4, max_rows, stream); break;
+    case kFmtBf16x3: launch_ln_fmt<kFmtBf16x3>(p, h4, max_rows, stream); break;
+    default: launch_ln_fmt<kFmtBf16x1>(p, h4, max_rows, stream); break;
   }
   ZETT_CUDA(cudaGetLastError());
   ++h->gemm.launches;
@@ -702,19 +716,31 @@ int launch_ln(zett_hn* h, LnParams p, long long max_rows, cudaStream_t stream) {
   return ZETT_OK;
 }
 
-int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
-  const int lph = std::min(32, h->dh / 4);  // lanes per head: each lane holds 4 consecutive elements (16-byte loads)
+template <int FMT>
+bool launch_attention_fmt(const AttnParams& p, int dh, cudaStream_t stream) {
+  // lanes per head x float4 per lane (kernels.cuh): eight lanes per head from dh = 64 up
+  const int lph = dh >= 256 ? 16 : 8;
   const int hpw = 32 / lph;
   const long long warps = static_cast<long long>(p.n_rows) * ((p.n_heads + hpw - 1) / hpw);
-  if (warps == 0) return ZETT_OK;
   const int grid = static_cast<int>((warps + 7) / 8);
-  switch (h->dh) {
-    case 32: attention_kernel<8, 1><<<grid, 256, 0, stream>>>(p); break;
-    case 64: attention_kernel<16, 1><<<grid, 256, 0, stream>>>(p); break;
-    case 128: attention_kernel<32, 1><<<grid, 256, 0, stream>>>(p); break;
-    case 256: attention_kernel<32, 2><<<grid, 256, 0, stream>>>(p); break;
-    default: return fail(ZETT_ERR_UNSUPPORTED, "attention head size must be 32, 64, 128 or 256");
+  switch (dh) {
+    case 32: attention_kernel<8, 1, FMT><<<grid, 256, 0, stream>>>(p); return true;
+    case 64: attention_kernel<8, 2, FMT><<<grid, 256, 0, stream>>>(p); return true;
+    case 128: attention_kernel<8, 4, FMT><<<grid, 256, 0, stream>>>(p); return true;
+    case 256: attention_kernel<16, 4, FMT><<<grid, 256, 0, stream>>>(p); return true;
+    default: return false;
   }
+}
+
+int launch_attention(zett_hn* h, const AttnParams& p, cudaStream_t stream) {
+  if (p.n_rows == 0 || p.n_heads == 0) return ZETT_OK;
+  bool ok;
+  switch (p.out.fmt) {
+    case kFmtF16F8: ok = launch_attention_fmt<kFmtF16F8>(p, h->dh, stream); break;
+    case kFmtBf16x3: ok = launch_attention_fmt<kFmtBf16x3>(p, h->dh, stream); break;
+    default: ok = launch_attention_fmt<kFmtBf16x1>(p, h->dh, stream); break;
+  }
+  if (!ok) return fail(ZETT_ERR_UNSUPPORTED, "attention head size must be 32, 64, 128 or 256");
   ZETT_CUDA(cudaGetLastError());
   ++h->gemm.launches;
   return ZETT_OK;
@@ -994,7 +1020,7 @@ int zett_hn_create(const zett_hn_config* cfg, zett_hn** out) {
   if (cfg->hn_surface_maxlen < 1 || cfg->hn_surface_maxlen > kMaxSurfaceLen - 1)
     return fail(ZETT_ERR_INVALID, "hn_surface_maxlen must be in [1, 31]");
   if (H % 8 || I % 8 || D % 8) return fail(ZETT_ERR_INVALID, "n_embd, hn_hidden_size, hn_intermediate_size must be multiples of 8");
-  if (H / 4 > kLnMaxVec * 256) return fail(ZETT_ERR_INVALID, "hn_hidden_size too large for the LayerNorm kernel (max 8192)");
+  if (H / 4 > kLnBlockVec * 256) return fail(ZETT_ERR_INVALID, "hn_hidden_size too large for the LayerNorm kernel (max 8192)");
   const int heads = cfg->hn_num_attention_heads > 0 ? cfg->hn_num_attention_heads : H / 64;
   if (heads <= 0 || H % heads) return fail(ZETT_ERR_INVALID, "hn_hidden_size must be divisible by the number of heads");
   const int dh = H / heads;

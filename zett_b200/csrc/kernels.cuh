@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rescale_kernel(const Ga
 // compact [n_rows, H] buffers (the pruned last layer reads only those), optionally a dot product with a vector
 // (bias_projection, modeling_hypernet.py:260-265).
 // -------------------------------------------------------------------------------------------------------------------
-constexpr int kLnMaxVec = 8;    // block per row: float4 per thread, H <= 4 * 8 * blockDim
+constexpr int kLnBlockVec = 8;  // block per row: float4 per thread; 128 threads up to H = 4096, 256 up to H = 8192
 constexpr int kLnWarpVec = 16;  // warp per row: float4 per lane, H <= 4 * 16 * 32 = 2048
 
 struct LnParams {
@@ -347,10 +347,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 // WARP = false: one block per row (H up to 4 * VEC * blockDim), block-wide reductions.
 // WARP = true : one warp per row (H up to 128 * VEC), shuffle reductions only -- rows of a few KB (H <= 2048) are
 //               latency-bound on the two block barriers otherwise (43 % of the HBM roofline at H = 768).
+// FMT is the operand format of out_op / c_op as a compile-time constant, and VEC is sized to the row by the launcher:
+// with the format read from the struct and VEC = 8 for every block-per-row shape the kernel executed ~200 instructions
+// per float4 (three pack variants behind uniform branches, twice; half of the unrolled loop dead) and ran at 58 % of
+// the SM's issue rate and 35 % of HBM -- issue-bound, not memory-bound (profiles/layernorm_r2_before.csv).
 // (minimum blocks per SM: without it ptxas hoists every gamma / beta / table load of the unrolled store loop to the top --
-// 196 registers, ONE resident block per SM, 13 % of the HBM rate; four blocks of <= 64 registers have no spills.  The
-// 16-float4-per-lane warp variant keeps its row in 64 registers and gets two.)
-template <bool WARP, int VEC>
+// 196 registers, ONE resident block per SM, 13 % of the HBM rate.  64 registers: four 256-thread or eight 128-thread
+// blocks; the 16-float4-per-lane warp variant keeps its row in 64 registers and gets two.)
+template <bool WARP, int VEC, int FMT>
 __global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : 4) layernorm_kernel(const LnParams p) {
   __shared__ float red[32];
   const int n = p.n_dev ? *p.n_dev : p.n_host;
@@ -359,74 +363,95 @@ __global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : 4) layernorm_kern
   const int row_threads = WARP ? 32 : blockDim.x;
   const int rows_per_block = WARP ? (blockDim.x >> 5) : 1;
   auto row_sum = [&](float v) { return WARP ? warp_sum(v) : block_sum(v, red); };
+  const float fh = static_cast<float>(p.H);
+  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(p.beta);
+  const float4* w4 = p.dot_w ? reinterpret_cast<const float4*>(p.dot_w) : nullptr;
+  const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) : nullptr;
   uint32_t bad = 0;
   for (int t = blockIdx.x * rows_per_block + (WARP ? (threadIdx.x >> 5) : 0); t < n; t += gridDim.x * rows_per_block) {
     float4 v[VEC];
     const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(p.in_index ? __ldg(p.in_index + t) : t) * p.lda);
     const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res + static_cast<long long>(t) * p.H) : nullptr;
-    const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) : nullptr;
     const float4* e4 = nullptr;
     if (p.table) {
       const int idx = p.table_idx ? __ldg(p.table_idx + t) : p.table_const;
       e4 = reinterpret_cast<const float4*>(p.table + static_cast<long long>(idx) * p.H);
     }
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) {
-      const int i = lane_in_row + c * row_threads;
-      if (i < H4) {
-        float4 x = a4[i];
-        if (r4) { const float4 y = r4[i]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-        if (z4) { const float4 y = __ldg(z4 + i); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-        if (e4) { const float4 y = __ldg(e4 + i); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-        v[c] = x;
-        s += (x.x + x.y) + (x.z + x.w);
-      }
-    }
-    const float mean = row_sum(s) / static_cast<float>(p.H);
-    float q = 0.f;
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) {
-      const int i = lane_in_row + c * row_threads;
-      if (i < H4) {
-        const float dx = v[c].x - mean, dy = v[c].y - mean, dz = v[c].z - mean, dw = v[c].w - mean;
-        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-      }
-    }
-    const float var = row_sum(q) / static_cast<float>(p.H);
-    const float rstd = 1.0f / sqrtf(var + p.eps);
-
+    // everything the store phase needs that does not depend on the statistics, fetched while the row is in flight
     const long long orow = p.out_index ? __ldg(p.out_index + t) : t;
-    const long long o = orow * p.H;
     long long crow = -1;
     if (p.tok_row) {
       const int r = __ldg(p.tok_row + t);
       if (__ldg(p.row_start + r) == t) crow = r;
     }
-    const long long co = crow * p.H;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      const int i = lane_in_row + c * row_threads;
+      if (i < H4) v[c] = a4[i];
+    }
+    if (r4) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const int i = lane_in_row + c * row_threads;
+        if (i < H4) { const float4 y = r4[i]; v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
+      }
+    }
+    if (z4) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const int i = lane_in_row + c * row_threads;
+        if (i < H4) { const float4 y = __ldg(z4 + i); v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
+      }
+    }
+    if (e4) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const int i = lane_in_row + c * row_threads;
+        if (i < H4) { const float4 y = __ldg(e4 + i); v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c)
+      if (lane_in_row + c * row_threads < H4) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    const float mean = row_sum(s) / fh;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      if (lane_in_row + c * row_threads < H4) {
+        v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
+        q += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
+      }
+    }
+    const float var = row_sum(q) / fh;
+    const float rstd = 1.0f / sqrtf(var + p.eps);
+
+    float* of = p.out_f32 ? p.out_f32 + orow * p.H : nullptr;
+    float* cf = (crow >= 0 && p.c_f32) ? p.c_f32 + crow * p.H : nullptr;
+    const bool has_op = p.out_op.base != nullptr, has_cop = crow >= 0 && p.c_op.base != nullptr;
     float dot = 0.f;
-    const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
-    const float4* b4 = reinterpret_cast<const float4*>(p.beta);
-    const float4* w4 = p.dot_w ? reinterpret_cast<const float4*>(p.dot_w) : nullptr;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
       const int i = lane_in_row + c * row_threads;
       if (i < H4) {
         const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
-        float4 y;
-        y.x = (v[c].x - mean) * rstd * g.x + b.x;
-        y.y = (v[c].y - mean) * rstd * g.y + b.y;
-        y.z = (v[c].z - mean) * rstd * g.z + b.z;
-        y.w = (v[c].w - mean) * rstd * g.w + b.w;
-        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o + 4 * i) = y;
-        if (p.out_op.base) store_split4(p.out_op, orow, 4 * i, y, false, bad);
-        if (crow >= 0) {
-          if (p.c_f32) *reinterpret_cast<float4*>(p.c_f32 + co + 4 * i) = y;
-          if (p.c_op.base) store_split4(p.c_op, crow, 4 * i, y, false, bad);
+        float y[4];
+        y[0] = v[c].x * rstd * g.x + b.x;
+        y[1] = v[c].y * rstd * g.y + b.y;
+        y[2] = v[c].z * rstd * g.z + b.z;
+        y[3] = v[c].w * rstd * g.w + b.w;
+        const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
+        if (of) reinterpret_cast<float4*>(of)[i] = y4;
+        if (cf) reinterpret_cast<float4*>(cf)[i] = y4;
+        if (has_op || has_cop) {
+          const Packed4 pk = pack_operand4(y, FMT, false, bad);
+          if (has_op) store_packed4_as<FMT>(p.out_op, orow, 4 * i, pk);
+          if (has_cop) store_packed4_as<FMT>(p.c_op, crow, 4 * i, pk);
         }
         if (w4) {
           const float4 w = __ldg(w4 + i);
-          dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
+          dot += (y[0] * w.x + y[1] * w.y) + (y[2] * w.z + y[3] * w.w);
         }
       }
     }
@@ -459,7 +484,11 @@ struct AttnParams {
   OperandOut out;                // [*, H] operand lines
 };
 
-template <int LPH, int VPL>
+// Lane mapping: with one float4 per lane (LPH = dh / 4) a key cost five shuffle + add steps and a full set of softmax
+// scalars for four FMAs of dot product, and the kernel ran at 77 % of the SM's issue rate (profiles/attention_r2_mistral.csv)
+// -- issue-bound.  Eight lanes per head with VPL float4 each (dh = 32 * VPL) need three shuffle steps per 4 * VPL FMAs and
+// share the scalars among four heads: 2.3x fewer instructions per (query, key, head) at dh = 128, 1.5x at dh = 64.
+template <int LPH, int VPL, int FMT>
 __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   constexpr int HPW = 32 / LPH;  // heads per warp
   const int lane = threadIdx.x & 31;
@@ -505,8 +534,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
         s *= p.scale;
       }
       const float m_new = fmaxf(m, s);
-      const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
-      const float w = expf(s - m_new);
+      const float corr = __expf(m - m_new);  // exp(-inf) = 0 on the first key
+      const float w = __expf(s - m_new);
       l = l * corr + w;
       const float* vj = p.v + kvj * p.ldv + hoff;
 #pragma unroll
@@ -523,7 +552,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
 #pragma unroll
       for (int d = 0; d < VPL; ++d) {
         const float y[4] = {acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv};
-        store_operand4(p.out, orow, hoff + 4 * LPH * d, y, false, bad);
+        store_packed4_as<FMT>(p.out, orow, hoff + 4 * LPH * d, pack_operand4(y, FMT, false, bad));
       }
     }
   }

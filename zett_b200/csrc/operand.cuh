@@ -121,6 +121,21 @@ __device__ __forceinline__ void store_packed4(const OperandOut& o, long long row
   }
 }
 
+// the same with the format as a compile-time constant (producers that are instantiated per format)
+template <int FMT>
+__device__ __forceinline__ void store_packed4_as(const OperandOut& o, long long row, int col, const Packed4& p) {
+  constexpr int kShift = FMT == kFmtBf16x1 ? 6 : 5;
+  const int e = col & ((1 << kShift) - 1);
+  uint8_t* line = o.base + row * o.ld_bytes + static_cast<long long>(col >> kShift) * 128;
+  *reinterpret_cast<uint2*>(line + 2 * e) = p.m;
+  if (FMT == kFmtF16F8) {
+    *reinterpret_cast<uint32_t*>(line + 64 + e) = p.s.x;
+    *reinterpret_cast<uint32_t*>(line + 96 + e) = p.t;
+  } else if (FMT == kFmtBf16x3) {
+    *reinterpret_cast<uint2*>(line + 64 + 2 * e) = p.s;
+  }
+}
+
 // 4 consecutive elements of a row (col a multiple of 4)
 __device__ __forceinline__ void store_operand4(const OperandOut& o, long long row, int col, const float* y, bool is_weight,
                                                uint32_t& bad) {
