@@ -59,12 +59,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 // arrive on the barrier at the same smem offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
@@ -125,36 +119,9 @@ constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
 
-// 3-D tiled load global -> this CTA's smem, completion on this CTA's mbarrier
-__device__ __forceinline__ void tma_load_3d(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
-}
-// 2-CTA variant: data lands in this CTA's smem, bytes are credited to the mbarrier of the pair's leader
-// (bit 24 of a shared::cluster address selects the CTA inside the pair; clearing it names CTA 0)
-__device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "l"(policy) : "memory");
-}
-// 2-CTA multicast variant: the box lands at the same smem offset in every CTA of `cta_mask` (cluster ranks), and each
-// destination's bytes are credited to the barrier at `bar`'s offset in the leader of THAT CTA's pair
-__device__ __forceinline__ void tma_load_3d_2sm_mc(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                                   uint16_t cta_mask, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-      " [%0], [%1, {%4, %5, %6}], [%2], %3, %7;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
-// 2-D tiled loads of operand lines (rows of 128-byte lines, uint8 tensor maps): {byte column, row}
-__device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
-}
-// CTA-pair variant: data lands in this CTA's smem, bytes are credited to the mbarrier of the pair's leader
+// 2-D tiled load of operand lines (rows of 128-byte lines, uint8 tensor maps): {byte column, row}.  CTA-pair form: data lands
+// in this CTA's smem, bytes are credited to the mbarrier of the pair's leader (bit 24 of a shared::cluster address selects
+// the CTA inside the pair; clearing it names CTA 0)
 __device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint32_t bar, uint32_t dst, int c0, int c1, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
@@ -246,19 +213,5 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (sm_100, version 1) of a K-major operand tile whose rows are `row_bytes` long and
-// swizzled with the matching TMA mode: 128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B, 32 B -> SWIZZLE_32B.  Rows are
-// grouped in 8-row atoms (stride byte offset = 8 * row_bytes); the leading byte offset is unused for swizzled K-major.
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t row_bytes) {
-  const uint64_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);        // start address            bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                            // leading byte offset      bits [16,30)
-  d |= static_cast<uint64_t>((8u * row_bytes) >> 4) << 32;        // stride byte offset       bits [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version
-  d |= layout << 61;                                              // swizzle mode
-  return d;
-}
 
 }  // namespace zett
