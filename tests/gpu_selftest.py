@@ -284,6 +284,36 @@ def run_sustained(mnk_list, seconds=1.5):
     return True
 
 
+RASTER_KEYS = ("ZETT_RASTER_CHUNK_MB", "ZETT_RASTER_GROUP_M", "ZETT_L2_HINT_A", "ZETT_L2_HINT_W")
+
+
+def run_raster(m, n, k, combos, impl=5, terms=2, seconds=1.2):
+    """Rasterisation / L2-hint probes of one GEMM shape under sustained load (no parity claim): `combos` is a list of
+    (chunk MB, m-group, hint A, hint W); hints 1 evict_first, 2 normal, 3 evict_last.  The same combinations go through
+    `one` under ncu for their DRAM traffic (scripts/gpu_r2k.sh)."""
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    a = torch.randn(m, k, device=dev)
+    w = torch.randn(n, k, device=dev) / k ** 0.5
+    out = torch.empty((m, n), device=dev)
+    b = torch.zeros(n, device=dev)
+    for combo in combos:
+        for key, val in zip(RASTER_KEYS, combo):
+            os.environ[key] = str(val)
+        ms, _ = _gemm_ex(lib, a, w, b, None, None, None, out, None, 0, impl, terms, iters=2)
+        iters = max(4, int(seconds * 1e3 / max(ms / 2, 1e-3)))
+        ps = PowerSampler()
+        ms, _ = _gemm_ex(lib, a, w, b, None, None, None, out, None, 0, impl, terms, iters=iters)
+        st = ps.stop()
+        t = ms / iters
+        print(json.dumps(dict(kind="raster", combo=list(combo), m=m, n=n, k=k, impl=impl, terms=terms, iters=iters, ms=round(t, 4),
+                              tflops_once=round(2.0 * m * n * k / (t * 1e-3) / 1e12, 1), **st)), flush=True)
+    for key in RASTER_KEYS:
+        os.environ.pop(key, None)
+    return True
+
+
 def run_one(m, n, k, impl, terms):
     lib = _lib.load()
     dev = torch.device("cuda", 0)
@@ -364,7 +394,8 @@ FORWARD_CASES = {
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["gemm", "forward", "sweep", "one", "sustained"])
+    ap.add_argument("what", choices=["gemm", "forward", "sweep", "one", "sustained", "raster"])
+    ap.add_argument("--combos", default="48,4,2,2", help="raster: semicolon-separated chunkMB,groupM,hintA,hintW")
     ap.add_argument("--mnk", default="16384,4096,4096")
     ap.add_argument("--impl", type=int, default=0)
     ap.add_argument("--configs", default="tiny,tiny_lang,tiny_single_head,tiny_plain,tiny_one_layer,tiny_multi_pass")
@@ -377,6 +408,9 @@ def main():
     elif args.what == "sweep":
         shapes = None if args.mnk == "16384,4096,4096" else [tuple(int(x) for x in t.split(",")) for t in args.mnk.split(";")]
         ok = run_sweep(shapes, terms_list=tuple(int(x) for x in args.sweep_terms.split(",")))
+    elif args.what == "raster":
+        m, n, k = [int(x) for x in args.mnk.split(",")]
+        ok = run_raster(m, n, k, [tuple(int(x) for x in c.split(",")) for c in args.combos.split(";")], args.impl or 5, args.terms or 2)
     elif args.what == "sustained":
         ok = run_sustained([tuple(int(x) for x in t.split(",")) for t in args.mnk.split(";")])
     elif args.what == "gemm":

@@ -506,6 +506,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const AttnParams p) {
   const bool any_valid = valid_mask != 0;
   const int n_q = p.row0_only ? 1 : n;
   uint32_t bad = 0;
+  // (Measured and not kept, round 2: prefetch.global.L1 of all of a row's K / V lines ahead of the query loop -- no change
+  // on any of the three shapes; 64 registers for four resident blocks at VPL = 4 -- inside the box-to-box noise.)
   // K and V are streamed per query (L1-resident re-reads).  Keeping a row's keys and values in registers (all loads issued
   // up front, 128 registers, two resident blocks per SM) was measured slower twice: round 1, and again in round 2 as a
   // separate kernel -- 15.4 vs 14.5 ms per XLM-R-shape step.
