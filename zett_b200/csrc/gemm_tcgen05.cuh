@@ -59,6 +59,8 @@ struct GemmShape {
   uint32_t idesc16;    // tcgen05 instruction descriptor, kind::f16
   uint32_t idesc8;     // tcgen05 instruction descriptor, kind::f8f6f4 (e5m2 x e5m2)
   unsigned long long* prof;  // nullable [gridDim.x, kProfSlots]
+  unsigned int* wave_sync;   // nullable [2], zero between launches: {arrivals, exits} of the producers' wave barrier
+  int sync_every;            // the producers of all CTAs meet every `sync_every` full waves of tiles (0: never)
 };
 
 struct TileCoord { int m_blk, n_blk; };
@@ -326,7 +328,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     long long waited = 0;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+    // Wave barrier.  The CTA pairs that share an A or W tile read it from L2 within microseconds of each other only while
+    // they run in lockstep; nothing keeps them there, and over the ~70 waves of a large GEMM they drift apart until a
+    // tile's second reader finds it evicted (DRAM reads per wave grow with the length of the launch:
+    // profiles/gemm_traffic_vs_n_r2.txt).  Every `sync_every` waves in which all pairs still have a tile, the producers
+    // meet before loading the next one.
+    const bool syncing = s.sync_every > 0 && s.wave_sync != nullptr;
+    const int full_iters = total_tiles / tile_step;
+    int iter = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
+      if (syncing && iter > 0 && iter < full_iters && iter % s.sync_every == 0) {
+        if (lane == 0) {
+          const unsigned int target = gridDim.x * static_cast<unsigned int>(iter / s.sync_every);
+          atomicAdd(s.wave_sync, 1u);
+          // best effort: the barrier only shapes the timing, so a producer that has waited 20 ms (CTAs not co-resident?)
+          // simply goes on
+          const unsigned long long t0 = globaltimer_ns();
+          while (*reinterpret_cast<volatile unsigned int*>(s.wave_sync) < target) {
+            __nanosleep(32);
+            if (globaltimer_ns() - t0 > 20000000ull) break;
+          }
+        }
+        __syncwarp();
+      }
       const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, s.group_m, s.chunk_n);
       const int row_a = tc.m_blk * tile_m + static_cast<int>(cta_rank) * kBlockM;
       const int row_b = tc.n_blk * tile_n + static_cast<int>(cta_rank) * load_n * HALVES;
@@ -347,6 +371,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
     if (prof && lane == 0) s.prof[static_cast<size_t>(blockIdx.x) * kProfSlots + 1] = static_cast<unsigned long long>(waited);
+    if (syncing && lane == 0) {
+      // the last producer to leave zeroes the counters for the next launch (everybody is past every barrier by then)
+      if (atomicAdd(s.wave_sync + 1, 1u) == gridDim.x - 1) {
+        s.wave_sync[0] = 0u;
+        s.wave_sync[1] = 0u;
+      }
+    }
   } else if (warp == 1) {
     // ===================================== MMA issuer ============================================
     if (leader) {

@@ -168,6 +168,8 @@ struct GemmEngine {
   uint64_t hint_a = kL2EvictNormal, hint_b = kL2EvictNormal;  // L2 eviction policies of the operand loads
   bool stream_out = false; // fp32 outputs stored with the streaming hint
   unsigned long long* prof_dev = nullptr;   // ZETT_GEMM_PROF=1: per-CTA stall counters of the last launch (probes)
+  unsigned int* wave_sync_dev = nullptr;    // counters of the producers' wave barrier (gemm_tcgen05.cuh), zero between launches
+  int sync_every = -1;                      // waves between two barriers: -1 sized per launch (~a barrier per 100 us), 0 none
   // optional per-launch timing (zett_hn_set_timing): event pairs recorded around every GEMM kernel
   bool timing = false;
   std::vector<cudaEvent_t> events;
@@ -185,6 +187,13 @@ struct GemmEngine {
     hint_a = hint(getenv("ZETT_L2_HINT_A"), hint_a);   // 1 evict_first, 2 normal, 3 evict_last
     hint_b = hint(getenv("ZETT_L2_HINT_W"), hint_b);
     if (const char* e = getenv("ZETT_STREAM_OUT")) stream_out = atoi(e) != 0;
+    if (const char* e = getenv("ZETT_GEMM_WAVE_SYNC")) sync_every = std::max(-1, atoi(e));
+    if (sync_every != 0 && !wave_sync_dev) {
+      if (cudaMalloc(&wave_sync_dev, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(wave_sync_dev, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+        cudaGetLastError();
+        wave_sync_dev = nullptr;   // the barrier is an optimisation: without its counters the kernels run unsynchronised
+      }
+    }
     if (getenv("ZETT_GEMM_PROF") && !prof_dev) {
       if (cudaMalloc(&prof_dev, sizeof(unsigned long long) * 256 * kProfSlots) != cudaSuccess) prof_dev = nullptr;
     }
@@ -196,6 +205,7 @@ struct GemmEngine {
   ~GemmEngine() {
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     if (prof_dev) cudaFree(prof_dev);
+    if (wave_sync_dev) cudaFree(wave_sync_dev);
   }
 
   int time_mark(cudaStream_t stream) {
@@ -311,6 +321,14 @@ struct GemmEngine {
     const int pairs = static_cast<int>(std::min<long long>(dev.num_sms / 2, tiles));
     cfg.gridDim = dim3(pairs * 2);
     s.prof = (prof_dev && pairs * 2 <= 256) ? prof_dev : nullptr;
+    // wave barrier of the producers (gemm_tcgen05.cuh): about one per 100 us of main loop -- every wave for 256 x 512 tiles
+    // at K = 4096 (~130 us per tile), every second for 256 x 256, every eleventh at K = 768; none for a single wave
+    s.wave_sync = wave_sync_dev;
+    s.sync_every = 0;
+    if (wave_sync_dev && tiles > pairs) {
+      const long long work = static_cast<long long>(s.k_lines) * s.block_n * halves;   // ~ main-loop time of one tile
+      s.sync_every = sync_every > 0 ? sync_every : (sync_every < 0 ? static_cast<int>(std::min<long long>(16, std::max<long long>(1, (65536 + work / 2) / std::max<long long>(work, 1)))) : 0);
+    }
     if (s.prof) ZETT_CUDA(cudaMemsetAsync(prof_dev, 0, sizeof(unsigned long long) * 256 * kProfSlots, stream));
     ZETT_TRY(time_mark(stream));
     if (fmt == kFmtF16F8) ZETT_TRY(launch_fmt<kFmtF16F8>(halves, cfg, *ta, *tb, s, ep));
