@@ -705,15 +705,16 @@ template <int FMT>
 void launch_ln_fmt(const LnParams& p, int h4, long long max_rows, cudaStream_t stream) {
   if (h4 <= 32 * kLnWarpVec) {  // one warp per row, eight rows per block
     const int grid = static_cast<int>(std::min<long long>((max_rows + 7) / 8, 148LL * 8));
-    if (h4 <= 32 * 4) layernorm_kernel<true, 4, FMT><<<grid, 256, 0, stream>>>(p);
-    else if (h4 <= 32 * 8) layernorm_kernel<true, 8, FMT><<<grid, 256, 0, stream>>>(p);
-    else layernorm_kernel<true, kLnWarpVec, FMT><<<grid, 256, 0, stream>>>(p);
+    if (h4 <= 32 * 4) layernorm_kernel<true, 4, FMT, 32><<<grid, 256, 0, stream>>>(p);
+    else if (h4 <= 32 * 8) layernorm_kernel<true, 8, FMT, 32, 3><<<grid, 256, 0, stream>>>(p);
+    else layernorm_kernel<true, kLnWarpVec, FMT, 32><<<grid, 256, 0, stream>>>(p);
   } else {
     // one block per row, eight float4 per thread: 128-thread blocks (eight resident per SM, so eight rows in different
     // phases of load / reduce / store) up to H = 4096, 256-thread blocks above
     const int threads = h4 <= 128 * kLnBlockVec ? 128 : 256;
     const int grid = static_cast<int>(std::min<long long>(max_rows, 148LL * (threads == 128 ? 32 : 16)));
-    layernorm_kernel<false, kLnBlockVec, FMT><<<grid, threads, 0, stream>>>(p);
+    if (threads == 128) layernorm_kernel<false, kLnBlockVec, FMT, 128, 3><<<grid, 128, 0, stream>>>(p);
+    else layernorm_kernel<false, kLnBlockVec, FMT, 256, 3><<<grid, 256, 0, stream>>>(p);
   }
 }
 

@@ -351,32 +351,38 @@ __device__ __forceinline__ float warp_sum(float v) {
 // with the format read from the struct and VEC = 8 for every block-per-row shape the kernel executed ~200 instructions
 // per float4 (three pack variants behind uniform branches, twice; half of the unrolled loop dead) and ran at 58 % of
 // the SM's issue rate and 35 % of HBM -- issue-bound, not memory-bound (profiles/layernorm_r2_before.csv).
-// (minimum blocks per SM: without it ptxas hoists every gamma / beta / table load of the unrolled store loop to the top --
-// 196 registers, ONE resident block per SM, 13 % of the HBM rate.  64 registers: four 256-thread or eight 128-thread
-// blocks; the 16-float4-per-lane warp variant keeps its row in 64 registers and gets two.)
-template <bool WARP, int VEC, int FMT>
-__global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : 4) layernorm_kernel(const LnParams p) {
+// (minimum blocks per SM, MINB: without a bound ptxas hoists every gamma / beta / table load of the unrolled store loop to
+// the top -- 196 registers, ONE resident block per SM, 13 % of the HBM rate.  Eight float4 per lane run best with three
+// blocks of <= 80 registers (at 64 they spill 16-24 bytes; XLM-R's LayerNorms 625 -> 568 us per pass), four float4 with
+// four blocks, the 16-float4-per-lane warp variant keeps its row in 64 registers and gets two.)
+// T = threads per row (32 for the warp form, the block size otherwise) is a template constant as well: the quads of a lane
+// are T apart, so every address of the row is "per-row base + lane offset" (computed once per row) plus a compile-time
+// multiple of 16 T bytes (fp32 rows and operand lines alike) -- no per-quad address arithmetic.
+template <bool WARP, int VEC, int FMT, int T, int MINB = 4>
+__global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : MINB) layernorm_kernel(const LnParams p) {
   __shared__ float red[32];
   const int n = p.n_dev ? *p.n_dev : p.n_host;
   const int H4 = p.H >> 2;
   const int lane_in_row = WARP ? (threadIdx.x & 31) : threadIdx.x;
-  const int row_threads = WARP ? 32 : blockDim.x;
-  const int rows_per_block = WARP ? (blockDim.x >> 5) : 1;
+  constexpr int rows_per_block = WARP ? 8 : 1;
   auto row_sum = [&](float v) { return WARP ? warp_sum(v) : block_sum(v, red); };
   const float fh = static_cast<float>(p.H);
-  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(p.beta);
-  const float4* w4 = p.dot_w ? reinterpret_cast<const float4*>(p.dot_w) : nullptr;
-  const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) : nullptr;
+  const float4* g4 = reinterpret_cast<const float4*>(p.gamma) + lane_in_row;
+  const float4* b4 = reinterpret_cast<const float4*>(p.beta) + lane_in_row;
+  const float4* w4 = p.dot_w ? reinterpret_cast<const float4*>(p.dot_w) + lane_in_row : nullptr;
+  const float4* z4 = p.vec0 ? reinterpret_cast<const float4*>(p.vec0) + lane_in_row : nullptr;
+  const bool has_op = p.out_op.base != nullptr;
+  // quads this lane owns: c < n_c  (lane_in_row + c * T < H4)
+  const int n_c = lane_in_row < H4 ? min(VEC, (H4 - lane_in_row + T - 1) / T) : 0;
   uint32_t bad = 0;
   for (int t = blockIdx.x * rows_per_block + (WARP ? (threadIdx.x >> 5) : 0); t < n; t += gridDim.x * rows_per_block) {
     float4 v[VEC];
-    const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(p.in_index ? __ldg(p.in_index + t) : t) * p.lda);
-    const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res + static_cast<long long>(t) * p.H) : nullptr;
+    const float4* a4 = reinterpret_cast<const float4*>(p.a + static_cast<long long>(p.in_index ? __ldg(p.in_index + t) : t) * p.lda) + lane_in_row;
+    const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res + static_cast<long long>(t) * p.H) + lane_in_row : nullptr;
     const float4* e4 = nullptr;
     if (p.table) {
       const int idx = p.table_idx ? __ldg(p.table_idx + t) : p.table_const;
-      e4 = reinterpret_cast<const float4*>(p.table + static_cast<long long>(idx) * p.H);
+      e4 = reinterpret_cast<const float4*>(p.table + static_cast<long long>(idx) * p.H) + lane_in_row;
     }
     // everything the store phase needs that does not depend on the statistics, fetched while the row is in flight
     const long long orow = p.out_index ? __ldg(p.out_index + t) : t;
@@ -386,40 +392,32 @@ __global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : 4) layernorm_kern
       if (__ldg(p.row_start + r) == t) crow = r;
     }
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) {
-      const int i = lane_in_row + c * row_threads;
-      if (i < H4) v[c] = a4[i];
-    }
+    for (int c = 0; c < VEC; ++c)
+      if (c < n_c) v[c] = a4[c * T];
     if (r4) {
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) {
-        const int i = lane_in_row + c * row_threads;
-        if (i < H4) { const float4 y = r4[i]; v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
-      }
+      for (int c = 0; c < VEC; ++c)
+        if (c < n_c) { const float4 y = r4[c * T]; v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
     }
     if (z4) {
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) {
-        const int i = lane_in_row + c * row_threads;
-        if (i < H4) { const float4 y = __ldg(z4 + i); v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
-      }
+      for (int c = 0; c < VEC; ++c)
+        if (c < n_c) { const float4 y = __ldg(z4 + c * T); v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
     }
     if (e4) {
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) {
-        const int i = lane_in_row + c * row_threads;
-        if (i < H4) { const float4 y = __ldg(e4 + i); v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
-      }
+      for (int c = 0; c < VEC; ++c)
+        if (c < n_c) { const float4 y = __ldg(e4 + c * T); v[c].x += y.x; v[c].y += y.y; v[c].z += y.z; v[c].w += y.w; }
     }
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < VEC; ++c)
-      if (lane_in_row + c * row_threads < H4) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+      if (c < n_c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
     const float mean = row_sum(s) / fh;
     float q = 0.f;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
-      if (lane_in_row + c * row_threads < H4) {
+      if (c < n_c) {
         v[c].x -= mean; v[c].y -= mean; v[c].z -= mean; v[c].w -= mean;
         q += (v[c].x * v[c].x + v[c].y * v[c].y) + (v[c].z * v[c].z + v[c].w * v[c].w);
       }
@@ -427,30 +425,32 @@ __global__ void __launch_bounds__(256, (WARP && VEC > 8) ? 2 : 4) layernorm_kern
     const float var = row_sum(q) / fh;
     const float rstd = 1.0f / sqrtf(var + p.eps);
 
-    float* of = p.out_f32 ? p.out_f32 + orow * p.H : nullptr;
-    float* cf = (crow >= 0 && p.c_f32) ? p.c_f32 + crow * p.H : nullptr;
-    const bool has_op = p.out_op.base != nullptr, has_cop = crow >= 0 && p.c_op.base != nullptr;
+    float4* of = p.out_f32 ? reinterpret_cast<float4*>(p.out_f32 + orow * p.H) + lane_in_row : nullptr;
+    float4* cf = (crow >= 0 && p.c_f32) ? reinterpret_cast<float4*>(p.c_f32 + crow * p.H) + lane_in_row : nullptr;
+    const bool has_cop = crow >= 0 && p.c_op.base != nullptr;
+    OperandCursor oc{nullptr, nullptr}, cc{nullptr, nullptr};
+    if (has_op) oc = operand_cursor<FMT>(p.out_op, orow, lane_in_row);
+    if (has_cop) cc = operand_cursor<FMT>(p.c_op, crow, lane_in_row);
     float dot = 0.f;
 #pragma unroll
     for (int c = 0; c < VEC; ++c) {
-      const int i = lane_in_row + c * row_threads;
-      if (i < H4) {
-        const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+      if (c < n_c) {
+        const float4 g = __ldg(g4 + c * T), b = __ldg(b4 + c * T);
         float y[4];
         y[0] = v[c].x * rstd * g.x + b.x;
         y[1] = v[c].y * rstd * g.y + b.y;
         y[2] = v[c].z * rstd * g.z + b.z;
         y[3] = v[c].w * rstd * g.w + b.w;
         const float4 y4 = make_float4(y[0], y[1], y[2], y[3]);
-        if (of) reinterpret_cast<float4*>(of)[i] = y4;
-        if (cf) reinterpret_cast<float4*>(cf)[i] = y4;
+        if (of) of[c * T] = y4;
+        if (cf) cf[c * T] = y4;
         if (has_op || has_cop) {
           const Packed4 pk = pack_operand4(y, FMT, false, bad);
-          if (has_op) store_packed4_as<FMT>(p.out_op, orow, 4 * i, pk);
-          if (has_cop) store_packed4_as<FMT>(p.c_op, crow, 4 * i, pk);
+          if (has_op) store_packed4_cursor<FMT>(oc, c * operand_quad_stride<FMT>(T), pk);
+          if (has_cop) store_packed4_cursor<FMT>(cc, c * operand_quad_stride<FMT>(T), pk);
         }
         if (w4) {
-          const float4 w = __ldg(w4 + i);
+          const float4 w = __ldg(w4 + c * T);
           dot += (y[0] * w.x + y[1] * w.y) + (y[2] * w.z + y[3] * w.w);
         }
       }

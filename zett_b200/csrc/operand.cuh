@@ -136,6 +136,36 @@ __device__ __forceinline__ void store_packed4_as(const OperandOut& o, long long 
   }
 }
 
+// A producer that walks a row in quads a fixed distance apart (LayerNorm: quad q, q + T, q + 2T ... with T a multiple of
+// 16) resolves the line arithmetic once: `m` points at the quad's main-plane bytes, `s` at its second-plane bytes, and
+// the quad `step` places further on sits operand_quad_stride<FMT>(T) * step bytes behind both.
+struct OperandCursor {
+  uint8_t* m;
+  uint8_t* s;
+};
+template <int FMT>
+__device__ __forceinline__ OperandCursor operand_cursor(const OperandOut& o, long long row, int quad) {
+  constexpr int kQuadsPerLine = FMT == kFmtBf16x1 ? 16 : 8;
+  uint8_t* line = o.base + row * o.ld_bytes + static_cast<long long>(quad / kQuadsPerLine) * 128;
+  const int e = quad % kQuadsPerLine;
+  OperandCursor c;
+  c.m = line + 8 * e;
+  c.s = line + 64 + (FMT == kFmtF16F8 ? 4 : 8) * e;
+  return c;
+}
+template <int FMT>
+__host__ __device__ constexpr int operand_quad_stride(int quads) { return quads * (FMT == kFmtBf16x1 ? 8 : 16); }
+template <int FMT>
+__device__ __forceinline__ void store_packed4_cursor(const OperandCursor& c, int byte_offset, const Packed4& p) {
+  *reinterpret_cast<uint2*>(c.m + byte_offset) = p.m;
+  if (FMT == kFmtF16F8) {
+    *reinterpret_cast<uint32_t*>(c.s + byte_offset) = p.s.x;
+    *reinterpret_cast<uint32_t*>(c.s + 32 + byte_offset) = p.t;
+  } else if (FMT == kFmtBf16x3) {
+    *reinterpret_cast<uint2*>(c.s + byte_offset) = p.s;
+  }
+}
+
 // 4 consecutive elements of a row (col a multiple of 4)
 __device__ __forceinline__ void store_operand4(const OperandOut& o, long long row, int col, const float* y, bool is_weight,
                                                uint32_t& bad) {
