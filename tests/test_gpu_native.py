@@ -218,6 +218,12 @@ def test_pipelined_tokens_path_equals_one_shot(torch_cuda):
     np.testing.assert_array_equal(sf2, sf)
     assert nt2 == n_trunc
     np.testing.assert_array_equal(out[:, :cfg.n_embd].numpy(), one[0])
+    # the first pass cut in two (the GPU starts after `first_chunk_rows` tokens): same rows, same bits
+    pipe = TokenPipeline(model, hn, src, rows_per_pass=400, first_chunk_rows=96)
+    out, sf2, nt2 = pipe.run(tokens)
+    np.testing.assert_array_equal(sf2, sf)
+    assert nt2 == n_trunc
+    np.testing.assert_array_equal(out[:, :cfg.n_embd].numpy(), one[0])
 
 
 @pytest.mark.parametrize("terms", [2, 3])

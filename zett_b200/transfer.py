@@ -233,7 +233,8 @@ def output_bias_of(model):
 class TokenPipeline:
     """Reusable buffers + streams for ``predict_from_tokens`` (one instance per hypernet / device)."""
 
-    def __init__(self, hypernet_or_native, hn_tokenizer, source_embeddings_dev, lang_index=None, rows_per_pass: int = 16384):
+    def __init__(self, hypernet_or_native, hn_tokenizer, source_embeddings_dev, lang_index=None, rows_per_pass: int = 16384,
+                 first_chunk_rows: int = 4096):
         from .surface_forms import native_model_for
         self.nat = hypernet_or_native.native() if hasattr(hypernet_or_native, "native") else hypernet_or_native
         self.cfg = self.nat.cfg
@@ -241,6 +242,10 @@ class TokenPipeline:
         self.src = source_embeddings_dev
         self.lang = -1 if (lang_index is None or not self.cfg.hn_embed_lang_id) else int(lang_index)
         self.rows_per_pass = int(rows_per_pass)
+        # the GPU idles while the very first pass is retokenised (nothing to overlap it with): that pass is cut in two so
+        # that the forward starts after `first_chunk_rows` tokens -- eight ranks sharing one host have two retokenizer
+        # threads each, and 16 384 tokens take them ~10 ms
+        self.first_chunk_rows = int(first_chunk_rows)
         self.tok_model = native_model_for(hn_tokenizer)
         self.pad_id = int(hn_tokenizer.pad_token_id)
         self.special = {t: int(hn_tokenizer.convert_tokens_to_ids(t)) for t in hn_tokenizer.all_special_tokens}
@@ -295,13 +300,17 @@ class TokenPipeline:
             if n_here <= 0:
                 break
             lo, hi = loc, loc + n_here
-            sf, nt = self.tok_model.surface_forms(tokens[lo:hi], cfg.hn_surface_maxlen, self.pad_id, special_tokens=self.special)  # host
-            n_trunc += nt
-            self.sf_pinned[lo:hi].numpy()[...] = sf
-            self.sf_dev[lo:hi].copy_(self.sf_pinned[lo:hi], non_blocking=True)                              # H2D
             blk = full[base + rank * per: base + rank * per + n_here]
-            self.nat.forward_into(self.sf_dev[lo:hi], self.src, self.lang, blk[:, 0:], blk[:, D:] if separate else None,
-                                  blk[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
+            c = self.first_chunk_rows
+            parts = [(lo, lo + c), (lo + c, hi)] if (loc == 0 and 0 < c and 2 * c <= n_here) else [(lo, hi)]
+            for a, b in parts:
+                sf, nt = self.tok_model.surface_forms(tokens[a:b], cfg.hn_surface_maxlen, self.pad_id, special_tokens=self.special)  # host
+                n_trunc += nt
+                self.sf_pinned[a:b].numpy()[...] = sf
+                self.sf_dev[a:b].copy_(self.sf_pinned[a:b], non_blocking=True)                              # H2D
+                part = blk[a - lo: b - lo]
+                self.nat.forward_into(self.sf_dev[a:b], self.src, self.lang, part[:, 0:], part[:, D:] if separate else None,
+                                      part[:, (2 if separate else 1) * D:], ld_pred=width, ld_bias=width)
             ev = torch.cuda.Event()
             ev.record(stream)
             if comm is not None and world > 1:                                                              # all-gather
