@@ -59,7 +59,7 @@ struct GemmShape {
   uint32_t idesc16;    // tcgen05 instruction descriptor, kind::f16
   uint32_t idesc8;     // tcgen05 instruction descriptor, kind::f8f6f4 (e5m2 x e5m2)
   unsigned long long* prof;  // nullable [gridDim.x, kProfSlots]
-  unsigned int* wave_sync;   // nullable [2], zero between launches: {arrivals, exits} of the producers' wave barrier
+  unsigned int* wave_sync;   // nullable [3], zero between launches: {arrivals, exits, gave up} of the producers' wave barrier
   int sync_every;            // the producers of all CTAs meet every `sync_every` full waves of tiles (0: never)
 };
 
@@ -340,13 +340,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (syncing && iter > 0 && iter < full_iters && iter % s.sync_every == 0) {
         if (lane == 0) {
           const unsigned int target = gridDim.x * static_cast<unsigned int>(iter / s.sync_every);
+          volatile unsigned int* ws = s.wave_sync;
           atomicAdd(s.wave_sync, 1u);
-          // best effort: the barrier only shapes the timing, so a producer that has waited 20 ms (CTAs not co-resident?)
-          // simply goes on
-          const unsigned long long t0 = globaltimer_ns();
-          while (*reinterpret_cast<volatile unsigned int*>(s.wave_sync) < target) {
-            __nanosleep(32);
-            if (globaltimer_ns() - t0 > 20000000ull) break;
+          // Best effort: the barrier only shapes the timing.  A wait is normally microseconds; a producer that has waited
+          // 2 ms (the CTAs are not all resident: SMs held by another kernel or process) switches the barrier off for the
+          // rest of this launch, for everybody.
+          if (ws[2] == 0u) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (ws[0] < target && ws[2] == 0u) {
+              __nanosleep(32);
+              if (globaltimer_ns() - t0 > 2000000ull) ws[2] = 1u;
+            }
           }
         }
         __syncwarp();
@@ -376,6 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (atomicAdd(s.wave_sync + 1, 1u) == gridDim.x - 1) {
         s.wave_sync[0] = 0u;
         s.wave_sync[1] = 0u;
+        s.wave_sync[2] = 0u;
       }
     }
   } else if (warp == 1) {

@@ -189,7 +189,7 @@ struct GemmEngine {
     if (const char* e = getenv("ZETT_STREAM_OUT")) stream_out = atoi(e) != 0;
     if (const char* e = getenv("ZETT_GEMM_WAVE_SYNC")) sync_every = std::max(-1, atoi(e));
     if (sync_every != 0 && !wave_sync_dev) {
-      if (cudaMalloc(&wave_sync_dev, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(wave_sync_dev, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+      if (cudaMalloc(&wave_sync_dev, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(wave_sync_dev, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
         cudaGetLastError();
         wave_sync_dev = nullptr;   // the barrier is an optimisation: without its counters the kernels run unsynchronised
       }
