@@ -474,7 +474,7 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
     # ---- end to end from host token strings ("e2e") -----------------------------------------------------------------
     e2e = None
     if want_e2e:
-        pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=P, first_chunk_rows=env_int("ZETT_BENCH_FIRST_CHUNK", 4096))
+        pipe = TokenPipeline(nat, hn, src, lang, rows_per_pass=P, first_chunk_rows=env_int("ZETT_BENCH_FIRST_CHUNK", -1) if "ZETT_BENCH_FIRST_CHUNK" in os.environ else None)
 
         def e2e_step():
             # host token strings -> native retokenizer -> pinned H2D -> forward into this rank's slots -> in-place all-gather

@@ -234,7 +234,7 @@ class TokenPipeline:
     """Reusable buffers + streams for ``predict_from_tokens`` (one instance per hypernet / device)."""
 
     def __init__(self, hypernet_or_native, hn_tokenizer, source_embeddings_dev, lang_index=None, rows_per_pass: int = 16384,
-                 first_chunk_rows: int = 4096):
+                 first_chunk_rows=None):
         from .surface_forms import native_model_for
         self.nat = hypernet_or_native.native() if hasattr(hypernet_or_native, "native") else hypernet_or_native
         self.cfg = self.nat.cfg
@@ -245,6 +245,12 @@ class TokenPipeline:
         # the GPU idles while the very first pass is retokenised (nothing to overlap it with): that pass is cut in two so
         # that the forward starts after `first_chunk_rows` tokens -- eight ranks sharing one host have two retokenizer
         # threads each, and 16 384 tokens take them ~10 ms
+        # (measured on one GPU: with two threads the cut saves 2.4 ms per 50k-token step; with sixteen threads the pass is
+        # retokenised in ~1.5 ms anyway and the cut COSTS 4 ms, because de-duplication works per pass -- so it is only made
+        # when the retokenizer is short of threads)
+        if first_chunk_rows is None:
+            from .surface_forms import default_threads
+            first_chunk_rows = 4096 if default_threads() <= 4 else 0
         self.first_chunk_rows = int(first_chunk_rows)
         self.tok_model = native_model_for(hn_tokenizer)
         self.pad_id = int(hn_tokenizer.pad_token_id)
