@@ -359,7 +359,8 @@ def measure(d, name, args, rows=None, vocab="random", hn_kind=None, env=None, wa
     if world > 1:
         transport = os.environ.get("ZETT_GATHER", "p2p")
         if transport == "p2p":   # peer copies over NVLink (copy engines) instead of ncclAllGather: the GEMMs keep every SM
-            d.comm.register(full)
+            if not d.comm.register(full):
+                transport = "nccl"   # a rank could not export / map the buffers: the library's ncclAllGather transport
 
     def slot_of(base, per, n_here):
         return full[base + rank * per: base + rank * per + n_here]

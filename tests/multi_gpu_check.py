@@ -41,7 +41,7 @@ def main():
             if transport == "p2p":   # registered full matrix: the gather becomes peer copies over NVLink
                 full = torch.zeros((parallel.padded_rows(rows, world, rpp), parallel.packed_width(cfg.n_embd, bool(cfg.separate_out_embeddings))),
                                    dtype=torch.float32, device=dev)
-                comm.register(full)
+                assert comm.register(full), "peer registration failed on this box"
             sharded = parallel.predict_sharded(rows, cfg.n_embd, bool(cfg.separate_out_embeddings), fn, dev, comm=comm,
                                                rows_per_pass=rpp, full=full)
             torch.cuda.synchronize()

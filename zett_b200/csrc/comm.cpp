@@ -177,7 +177,10 @@ int zett_comm_ipc_handle(const void* dev_ptr, void* out_handle_64_bytes, int64_t
     return fail(ZETT_ERR_CUDA, "cuMemGetAddressRange failed: not a device allocation");
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
-  if (e != cudaSuccess) return fail(ZETT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ZETT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
   memcpy(out_handle_64_bytes, &h, 64);
   *out_offset = static_cast<int64_t>(reinterpret_cast<unsigned long long>(dev_ptr) - base);
   return ZETT_OK;
@@ -208,6 +211,7 @@ int zett_comm_register(zett_comm* c, void* full_dev, int64_t bytes, const void* 
     void* base = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
+      cudaGetLastError();   // not sticky: clear it, the caller falls back to the NCCL transport
       zett_comm_unregister(c);
       return fail(ZETT_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
     }

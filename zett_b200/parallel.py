@@ -104,20 +104,32 @@ class NativeComm:
         self._lib.check(self.lib.zett_allgather_rows(self.handle, ctypes.c_void_p(shard_ptr), per, width,
                                                      ctypes.c_void_p(full_slab.data_ptr()), ctypes.c_void_p(s)))
 
-    def register(self, full: torch.Tensor, group=None):
+    def register(self, full: torch.Tensor, group=None) -> bool:
         """Collective: from now on ``allgather_rows`` into ``full`` is peer copies (copy engines over NVLink, no kernel) instead
-        of ncclAllGather.  ``full`` must have the same size on every rank.  Handles travel over torch.distributed."""
+        of ncclAllGather.  ``full`` must have the same size on every rank.  Handles travel over torch.distributed.
+        Returns False -- on EVERY rank, with nothing registered -- when any rank cannot export or map the buffers (no peer
+        access, CUDA IPC not permitted in the container): the caller then simply keeps the ncclAllGather transport."""
         if self.world == 1:
-            return
+            return True
         handle, off = ctypes.create_string_buffer(64), ctypes.c_int64(0)
-        self._lib.check(self.lib.zett_comm_ipc_handle(ctypes.c_void_p(full.data_ptr()), handle, ctypes.byref(off)))
+        rc = self.lib.zett_comm_ipc_handle(ctypes.c_void_p(full.data_ptr()), handle, ctypes.byref(off))
         box = [None] * self.world
-        dist.all_gather_object(box, (handle.raw, int(off.value)), group=group)
+        dist.all_gather_object(box, (handle.raw, int(off.value)) if rc >= 0 else None, group=group)
+        if any(b is None for b in box):
+            return False
         blob = b"".join(h for h, _ in box)
         offs = (ctypes.c_int64 * self.world)(*[o for _, o in box])
-        self._lib.check(self.lib.zett_comm_register(self.handle, ctypes.c_void_p(full.data_ptr()), full.numel() * full.element_size(),
-                                                    blob, offs))
+        rc = self.lib.zett_comm_register(self.handle, ctypes.c_void_p(full.data_ptr()), full.numel() * full.element_size(), blob, offs)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, rc >= 0, group=group)
+        if not all(oks):
+            if rc >= 0:
+                torch.cuda.synchronize(full.device)
+                self.lib.zett_comm_unregister(self.handle)
+            dist.barrier(group=group)
+            return False
         self._registered = full   # keep the tensor alive while peers map it
+        return True
 
     def unregister(self, group=None):
         if self.world > 1 and getattr(self, "_registered", None) is not None:
