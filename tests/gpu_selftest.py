@@ -215,8 +215,8 @@ class PowerSampler:
 
 def run_sustained(mnk_list, seconds=1.5):
     """Energy / throughput probes (no parity claim): every operand format and cluster shape launched back to back for
-    ~`seconds`, with board power and SM clock sampled meanwhile; ZETT_MMA_MASK variants drop product terms to separate the
-    cost of the MMAs from the cost of moving the operands.  A cuBLAS bf16 matmul of the same shape runs beside them."""
+    ~`seconds`, with board power and SM clock sampled meanwhile (act 0x100 = no stores, to separate the cost of the epilogue's
+    output from the main loop).  A cuBLAS bf16 matmul of the same shape runs beside them."""
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
